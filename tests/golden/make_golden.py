@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the REFERENCE's own Python functions (imported read-only
+from /root/reference) on small seeded inputs, and assert on the spot that oracle/ reproduces them.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    PYTHONDONTWRITEBYTECODE=1 python tests/golden/make_golden.py
+
+The committed .npz files are the contract that tests/test_oracle_golden.py (CPU) and the -m gpu parity
+tests replay.  The reference ships no tests or golden vectors of its own, so these
+recorded reference outputs are what pins the oracle.
+"""
+
+import ast
+import math
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.dont_write_bytecode = True
+sys.path.insert(0, REF)
+sys.path.insert(1, ROOT)
+
+from training import volumetric_rendering as ref_vr            # noqa: E402  (reference)
+from dnnlib.util import sample_from_triplane as ref_triplane    # noqa: E402
+from torch_utils.ops import upfirdn2d as ref_up                 # noqa: E402
+from torch_utils.ops import bias_act as ref_ba                  # noqa: E402
+from torch_utils.ops import filtered_lrelu as ref_fl            # noqa: E402
+from torch_utils.ops import conv2d_resample as ref_cr           # noqa: E402
+
+import oracle                                                    # noqa: E402
+from oracle import renderer as orr, ops as oops, camera as ocam  # noqa: E402
+
+DEV = torch.device('cpu')
+
+
+def t2n(d):
+    return {k: (v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in d.items()}
+
+
+def save(name, **arrs):
+    path = os.path.join(HERE, name + '.npz')
+    np.savez_compressed(path, **t2n(arrs))
+    print(f'{name:24s} {os.path.getsize(path) / 1024:8.1f} KB')
+
+
+def close(a, b, tol=2e-6, what=''):
+    a = torch.as_tensor(a).double()
+    b = torch.as_tensor(b).double()
+    err = (a - b).abs().max().item() if a.numel() else 0.0
+    assert a.shape == b.shape and err <= tol, f'{what}: shape {tuple(a.shape)} vs {tuple(b.shape)} err {err:g}'
+    return err
+
+
+# ------------------------------------------------------------------ a1 rays
+def g_rays():
+    for tag, (n, S, fov, res, rs, re) in {'a': (2, 6, 18.0, (8, 8), 2.25, 3.3), 'b': (1, 5, 30.0, (6, 4), 0.5, 1.5)}.items():
+        p, z, d = ref_vr.get_initial_rays_trig(n, S, DEV, fov, res, rs, re)
+        po, zo, do = orr.initial_rays(n, S, fov, res, rs, re)
+        close(p, po, what='rays.points'); close(z, zo, what='rays.z'); close(d, do, what='rays.d')
+        save(f'rays_{tag}', n=n, num_steps=S, fov=fov, resolution=np.array(res), ray_start=rs, ray_end=re,
+             points=p, z_vals=z, rays_d_cam=d)
+
+
+# ------------------------------------------------------------------ a2+a3 jitter + world transform
+def g_transform():
+    n, S, res = 2, 6, (8, 8)
+    p, z, d = ref_vr.get_initial_rays_trig(n, S, DEV, 18.0, res, 2.25, 3.3)
+    cam = torch.from_numpy(ocam.look_at_pose(np.array([[1.2], [1.9]], np.float32), np.array([[1.4], [1.7]], np.float32),
+                                             [0, 0, 0.2], radius=2.7, batch_size=2))
+    torch.manual_seed(123)
+    u = torch.rand(z.shape)                      # what perturb_points will draw first (:101)
+    torch.manual_seed(123)
+    pw, zj, dw, ow, _pitch, _yaw = ref_vr.transform_sampled_points(p, z, d, DEV, camera=cam)
+    pj, zo = orr.perturb(p, z, d, u)
+    pwo, dwo, owo = orr.to_world(pj, d, cam)
+    close(zj, zo, what='xf.z'); close(pw, pwo, what='xf.pw'); close(dw, dwo, what='xf.dw'); close(ow, owo, what='xf.ow')
+    save('transform', points=p, z_vals=z, rays_d_cam=d, camera=cam, u=u, points_world=pw, z_jit=zj,
+         dirs_world=dw, origins_world=ow)
+
+
+# ------------------------------------------------------------------ a4 cameras
+def g_camera():
+    hs = np.array([math.pi / 2, 1.1, 2.0], np.float32)
+    vs = np.array([math.pi / 2, 1.3, 1.9], np.float32)
+    out = {}
+    for i, (h, v) in enumerate(zip(hs, vs)):
+        o, phi, th = ref_vr.sample_camera_positions(DEV, n=1, r=2.7, horizontal_mean=float(h), vertical_mean=float(v), mode=None)
+        oo, _, _ = ocam.sample_camera_positions(n=1, r=2.7, horizontal_mean=float(h), vertical_mean=float(v), mode=None)
+        close(o, oo, what='cam.origin')
+        m = ref_vr.create_cam2world_matrix(-o, o, device=DEV)
+        close(m, ocam.create_cam2world_matrix(-oo, oo), what='cam.c2w')
+        la = ref_vr.LookAtPoseSampler.sample(float(h), float(v), torch.tensor([0, 0, 0.2]), radius=2.7)
+        close(la, ocam.look_at_pose(float(h), float(v), [0, 0, 0.2], radius=2.7), what='cam.lookat')
+        out[f'origin{i}'] = o; out[f'c2w{i}'] = m; out[f'lookat{i}'] = la
+    save('camera', h=hs, v=vs, radius=2.7, lookat=np.array([0, 0, 0.2], np.float32), **out)
+
+
+# ------------------------------------------------------------------ a5 tri-plane gather
+def g_triplane():
+    g = torch.Generator().manual_seed(7)
+    grid = torch.randn(2, 96, 12, 12, generator=g)
+    coords = (torch.rand(2, 300, 3, generator=g) * 2.6 - 1.3)      # includes out-of-range taps
+    coords[0, :4] = torch.tensor([[-1., -1., -1.], [1., 1., 1.], [0., 0., 0.], [0.999, -0.999, 0.5]])
+    f = ref_triplane(coords, grid)
+    close(f, orr.sample_triplane(coords, grid), tol=3e-6, what='triplane')
+    close(f, orr.sample_triplane_torch(coords, grid), tol=1e-6, what='triplane_torch')
+    save('triplane', grid=grid, coords=coords, feat=f)
+
+
+# ------------------------------------------------------------------ a7 compositing
+def g_integration():
+    g = torch.Generator().manual_seed(11)
+    n, R, S, C = 2, 10, 12, 52
+    rgb_sigma = torch.randn(n, R, S, C, generator=g)
+    rgb_sigma[..., -1] *= 4
+    z = torch.sort(torch.rand(n, R, S, 1, generator=g) * 1.05 + 2.25, dim=2)[0]
+    d = torch.randn(n, R, 3, generator=g)
+    cases = {
+        'softplus': dict(clamp_mode='softplus'),
+        'relu': dict(clamp_mode='relu'),
+        'lastback': dict(clamp_mode='softplus', last_back=True),
+        'white': dict(clamp_mode='softplus', white_back=True, max_depth=3.5),
+        'fillw': dict(clamp_mode='relu', fill_mode='weight'),
+    }
+    out = {}
+    for k, kw in cases.items():
+        rgb, dep, w = ref_vr.fancy_integration(rgb_sigma.clone(), d, z, DEV, noise_std=0, **kw)
+        ro, do_, wo = orr.composite(rgb_sigma.clone(), d, z, **kw)
+        close(rgb, ro, tol=5e-6, what=k + '.rgb'); close(dep, do_, tol=5e-6, what=k + '.depth'); close(w, wo, what=k + '.w')
+        out[k + '_rgb'] = rgb; out[k + '_depth'] = dep; out[k + '_weights'] = w
+    save('integration', rgb_sigma=rgb_sigma, z_vals=z, rays_d_cam=d, **out)
+
+
+# ------------------------------------------------------------------ a8 importance sampling
+def g_pdf():
+    g = torch.Generator().manual_seed(5)
+    R, S = 9, 12
+    z = torch.sort(torch.rand(R, S, generator=g) + 2, dim=1)[0]
+    bins = 0.5 * (z[:, :-1] + z[:, 1:])            # [R, S-1]
+    w = torch.rand(R, S - 2, generator=g)
+    w[3] = 0                                        # a ray with zero weights
+    det = ref_vr.sample_pdf(bins, w, 8, det=True)
+    close(det, orr.sample_pdf(bins, w, 8, det=True), what='pdf.det')
+    torch.manual_seed(77)
+    u = torch.rand(R, 8)
+    torch.manual_seed(77)
+    rnd = ref_vr.sample_pdf(bins, w, 8, det=False)
+    close(rnd, orr.sample_pdf(bins, w, 8, det=False, u=u), what='pdf.rand')
+    save('sample_pdf', bins=bins, weights=w, det=det, u=u, rnd=rnd)
+
+
+# ------------------------------------------------------------------ composed chain (reference functions + decoder)
+def g_chain():
+    g = torch.Generator().manual_seed(3)
+    n, S, res = 2, 12, (8, 8)
+    tex = torch.randn(n, 96, 16, 16, generator=g)
+    seg = torch.randn(n, 96, 16, 16, generator=g)
+    dec = orr.Decoder.random(hidden=16, seed=4, three_head=True)
+    cam = torch.from_numpy(ocam.look_at_pose(np.array([[1.3], [1.8]], np.float32), np.array([[1.5], [1.65]], np.float32),
+                                             [0, 0, 0.2], radius=2.7, batch_size=2))
+    box_scale = 2.0
+    p, z, d = ref_vr.get_initial_rays_trig(n, S, DEV, 18.0, res, 2.25, 3.3)
+    torch.manual_seed(9)
+    u = torch.rand(z.shape)
+    torch.manual_seed(9)
+    pw, zj, dw, ow, _, _ = ref_vr.transform_sampled_points(p, z, d, DEV, camera=cam)
+    coords = pw.reshape(n, -1, 3) * box_scale
+    ft = ref_triplane(coords, tex)
+    fs = ref_triplane(coords, seg)
+    raw = dec(ft, fs).reshape(n, res[0] * res[1], S, 52)
+    rgb, dep, w = ref_vr.fancy_integration(raw, d, zj, DEV, noise_std=0, clamp_mode='softplus')
+    ro, do_, wo = orr.render_frames(tex, seg, dec, cam, fov=18.0, num_steps=S, ray_start=2.25, ray_end=3.3,
+                                    resolution=res, box_scale=box_scale, jitter_u=u)
+    close(rgb, ro, tol=1e-5, what='chain.rgb'); close(dep, do_, tol=1e-5, what='chain.depth'); close(w, wo, tol=1e-5, what='chain.w')
+    save('chain', planes_tex=tex, planes_seg=seg, w1=dec.w1, b1=dec.b1, w2=dec.w2, b2=dec.b2, camera=cam, u=u,
+         box_scale=box_scale, num_steps=S, resolution=np.array(res), rgb=rgb, depth=dep, weights=w,
+         raw=raw, points_world=pw)
+    # sigma-only voxel query on the same planes (sample_voxel contract, extract_shapes.py:146)
+    pts = torch.rand(n, 50, 3, generator=g) - 0.5
+    sv = dec(ref_triplane(pts * box_scale, tex), ref_triplane(pts * box_scale, seg)).reshape(n, 50, 52)
+    close(sv, orr.sample_voxel(tex, seg, dec, pts, box_scale), tol=1e-5, what='voxel')
+    save('voxel', points=pts, out=sv)
+
+
+# ------------------------------------------------------------------ create_samples quirk
+def g_create_samples():
+    src = open(os.path.join(REF, 'extract_shapes.py')).read()
+    fn = [n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == 'create_samples'][0]
+    ns = {'np': np, 'torch': torch}
+    exec(compile(ast.Module([fn], []), 'extract_shapes.py', 'exec'), ns)     # run the reference's own function
+    s, origin, vs = ns['create_samples'](N=8, voxel_origin=[0, 0, 0], cube_length=1.0)
+    so, oo, vo = orr.create_samples(8, [0, 0, 0], 1.0)
+    close(s, so, what='create_samples')
+    save('create_samples', N=8, cube_length=1.0, samples=s, origin=origin, voxel_size=vs)
+
+
+# ------------------------------------------------------------------ ops
+def g_bias_act():
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(3, 5, 4, 6, generator=g) * 3
+    b = torch.randn(5, generator=g)
+    out = {}
+    for act in ref_ba.activation_funcs:
+        for tag, kw in {'d': {}, 'c': dict(alpha=0.3, gain=1.7, clamp=0.9)}.items():
+            y = ref_ba.bias_act(x, b, dim=1, act=act, impl='ref', **kw)
+            close(y, oops.bias_act(x, b, 1, act, **kw), what=f'bias_act.{act}.{tag}')
+            out[f'{act}_{tag}'] = y
+    xl = torch.randn(7, 5, generator=g)
+    out['dim1_2d'] = ref_ba.bias_act(xl, b, dim=1, act='lrelu', impl='ref')
+    out['nobias'] = ref_ba.bias_act(x, None, act='swish', impl='ref')
+    save('bias_act', x=x, b=b, x2d=xl, **out)
+
+
+UPFIR_CASES = {
+    # name: (filter taps or 2-D, up, down, padding, flip, gain)
+    'up2_4x4': ([1, 3, 3, 1], 2, 1, [2, 1, 2, 1], False, 4.0),
+    'down2_4x4': ([1, 3, 3, 1], 1, 2, [1, 1, 1, 1], False, 1.0),
+    'filt_4x4': ([1, 3, 3, 1], 1, 1, [1, 1, 1, 1], False, 4.0),     # the conv-up post filter
+    'filt_flip': ([1, 2, 4, 3], 1, 1, [2, 1, 2, 1], True, 1.0),
+    'asym': ([[1, 2, 0], [0, 3, 1]], (2, 1), (1, 2), [3, 0, -1, 2], False, 0.5),
+    'sep8': ([1, 2, 3, 4, 4, 3, 2, 1], 2, 2, [3, 4, 4, 3], False, 1.0),
+    'up4_down1': ([1, 4, 6, 4, 1], (4, 4), (1, 1), [2, 2, 2, 2], False, 16.0),
+    'crop': ([1, 1], 1, 1, [-1, -2, 0, -1], False, 1.0),
+    'ident': (None, 1, 1, 0, False, 1.0),
+}
+
+
+def g_upfirdn2d():
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(2, 3, 9, 7, generator=g)
+    out = {}
+    for name, (taps, up, down, pad, flip, gain) in UPFIR_CASES.items():
+        f = None if taps is None else ref_up.setup_filter(taps)
+        if f is not None:
+            close(f, oops.setup_filter(taps), what='setup_filter.' + name)
+        y = ref_up.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=flip, gain=gain, impl='ref')
+        close(y, oops.upfirdn2d(x, f, up=up, down=down, padding=pad, flip_filter=flip, gain=gain), tol=3e-6, what='upfirdn2d.' + name)
+        if f is not None and f.ndim == 2:
+            upp = (up, up) if isinstance(up, int) else up
+            dnn = (down, down) if isinstance(down, int) else down
+            close(y, oops.upfirdn2d_direct(x, f, upp, dnn, oops._pad4(pad), flip, gain), tol=3e-6, what='direct.' + name)
+        out[name] = y
+        if f is not None:
+            out[name + '_f'] = f
+    f = ref_up.setup_filter([1, 3, 3, 1])
+    out['upsample2d'] = ref_up.upsample2d(x, f, impl='ref'); close(out['upsample2d'], oops.upsample2d(x, f), tol=3e-6, what='upsample2d')
+    out['downsample2d'] = ref_up.downsample2d(x, f, impl='ref'); close(out['downsample2d'], oops.downsample2d(x, f), tol=3e-6, what='downsample2d')
+    out['filter2d'] = ref_up.filter2d(x, f, impl='ref'); close(out['filter2d'], oops.filter2d(x, f), tol=3e-6, what='filter2d')
+    save('upfirdn2d', x=x, **out)
+
+
+def g_filtered_lrelu():
+    import scipy.signal
+    g = torch.Generator().manual_seed(41)
+    x = torch.randn(2, 3, 16, 16, generator=g) * 2
+    b = torch.randn(3, generator=g)
+    f12 = torch.as_tensor(scipy.signal.firwin(numtaps=12, cutoff=0.25, width=0.5), dtype=torch.float32)
+    f2d = torch.outer(f12[:8], f12[:8]); f2d = f2d / f2d.sum()
+    cases = {
+        'su2_sd2': dict(fu=f12 * 2 ** 0, fd=f12, up=2, down=2, padding=[5, 6, 5, 6], clamp=1.5),
+        'su2_sd1': dict(fu=f12, fd=None, up=2, down=1, padding=[5, 6, 5, 6], clamp=None),
+        'su1_sd2': dict(fu=None, fd=f12, up=1, down=2, padding=[5, 6, 5, 6], clamp=2.0, slope=0.1, gain=1.3),
+        'fu2_fd2': dict(fu=f2d, fd=f2d, up=2, down=2, padding=[7, 8, 7, 8], clamp=1.0, flip_filter=True),
+        'su4_sd2': dict(fu=torch.cat([f12, f12]) / 2, fd=f12, up=4, down=2, padding=[17, 18, 17, 18], clamp=0.8),
+        'plain': dict(fu=None, fd=None, up=1, down=1, padding=0, clamp=0.7),
+    }
+    out = {}
+    for k, kw in cases.items():
+        y = ref_fl.filtered_lrelu(x, b=b, impl='ref', **kw)
+        close(y, oops.filtered_lrelu(x, b=b, **kw), tol=5e-6, what='flrelu.' + k)
+        out[k] = y
+        for a in ('fu', 'fd'):
+            if kw[a] is not None:
+                out[f'{k}_{a}'] = kw[a]
+    save('filtered_lrelu', x=x, b=b, **out)
+
+
+def g_conv2d_resample():
+    g = torch.Generator().manual_seed(51)
+    x = torch.randn(2, 4, 8, 8, generator=g)
+    w3 = torch.randn(6, 4, 3, 3, generator=g)
+    w1 = torch.randn(6, 4, 1, 1, generator=g)
+    wg = torch.randn(6, 2, 3, 3, generator=g)
+    f = ref_up.setup_filter([1, 3, 3, 1])
+    cases = {
+        'up2_k3': dict(w=w3, f=f, up=2, padding=1, flip_weight=False),
+        'up2_k3_g2': dict(w=wg, f=f, up=2, padding=1, groups=2, flip_weight=False),
+        'same_k3': dict(w=w3, padding=1),
+        'down2_k3': dict(w=w3, f=f, down=2, padding=1),
+        'up2_k1': dict(w=w1, f=f, up=2),
+        'down2_k1': dict(w=w1, f=f, down=2),
+    }
+    out = {}
+    for k, kw in cases.items():
+        y = ref_cr.conv2d_resample(x, **kw)
+        close(y, oops.conv2d_resample(x, **kw), tol=3e-5, what='conv2d_resample.' + k)
+        out[k] = y
+    save('conv2d_resample', x=x, w3=w3, w1=w1, wg=wg, f=f, **out)
+
+
+if __name__ == '__main__':
+    torch.set_num_threads(4)
+    for fn in (g_rays, g_transform, g_camera, g_triplane, g_integration, g_pdf, g_chain, g_create_samples,
+               g_bias_act, g_upfirdn2d, g_filtered_lrelu, g_conv2d_resample):
+        fn()
+    print('all reference outputs reproduced by oracle/ within tolerance')
