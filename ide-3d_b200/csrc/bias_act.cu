@@ -1,0 +1,211 @@
+// bias_act for sm_100a: y = clamp(gain * act(x + b)) plus the 1st/2nd-order gradient forms.
+// Replaces bias_act_kernel<T,A> (torch_utils/ops/bias_act.cu:23-147) behind the same parameter set
+// (bias_act.h:12-31).  Pure HBM stream: 2 * size_x * sizeof(T) algorithmic bytes (+ aux tensors for
+// the gradient forms).  128-bit loads/stores, 4 vectors in flight per thread, 64-bit indexing, grid
+// sized to the SM count (grid-stride loop).
+#include "common.cuh"
+
+namespace ide3d {
+
+struct BiasActArgs {
+    const void *x, *b, *xref, *yref, *dy;
+    void* y;
+    int grad;
+    float alpha, gain, clamp;
+    long long size_x, size_b, step_b;
+};
+
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+
+template <typename S> __device__ __forceinline__ S exp_(S v);
+template <> __device__ __forceinline__ float exp_<float>(float v) { return __expf(v); }
+template <> __device__ __forceinline__ double exp_<double>(double v) { return exp(v); }
+template <typename S> __device__ __forceinline__ S log_(S v);
+template <> __device__ __forceinline__ float log_<float>(float v) { return __logf(v); }
+template <> __device__ __forceinline__ double log_<double>(double v) { return log(v); }
+
+// One element.  G = 0 forward; G = 1: x carries dy, result is dx; G = 2: second-order term.
+// Case analysis follows bias_act.cu:57-129 (expRange 80, halfExpRange 40, selu constants).
+template <typename S, int A>
+__device__ __forceinline__ S eval(S x, S b, S xref, S yref, S dy, int G, S alpha, S gain, S clamp) {
+    const S one = (S)1, two = (S)2, expRange = (S)80, halfExpRange = (S)40;
+    const S seluScale = (S)1.0507009873554804934193349852946, seluAlpha = (S)1.6732632423543772848170429916717;
+    const S yy = (gain != (S)0) ? yref / gain : (S)0;
+    S y = 0;
+    if (G == 0) x += b; else xref += b;
+    if (A == 1) { y = x; if (G == 2) y = 0; }
+    if (A == 2) { if (G == 0) y = (x > 0) ? x : 0; if (G == 1) y = (yy > 0) ? x : 0; }
+    if (A == 3) { if (G == 0) y = (x > 0) ? x : x * alpha; if (G == 1) y = (yy > 0) ? x : x * alpha; }
+    if (A == 4) {
+        if (G == 0) { const S c = exp_(x), d = one / c; y = (x < -expRange) ? -one : (x > expRange) ? one : (c - d) / (c + d); }
+        if (G == 1) y = x * (one - yy * yy);
+        if (G == 2) y = x * (one - yy * yy) * (-two * yy);
+    }
+    if (A == 5) {
+        if (G == 0) y = (x < -expRange) ? 0 : one / (exp_(-x) + one);
+        if (G == 1) y = x * yy * (one - yy);
+        if (G == 2) y = x * yy * (one - yy) * (one - two * yy);
+    }
+    if (A == 6) {
+        if (G == 0) y = (x >= 0) ? x : exp_(x) - one;
+        if (G == 1) y = (yy >= 0) ? x : x * (yy + one);
+        if (G == 2) y = (yy >= 0) ? 0 : x * (yy + one);
+    }
+    if (A == 7) {
+        if (G == 0) y = (x >= 0) ? seluScale * x : (seluScale * seluAlpha) * (exp_(x) - one);
+        if (G == 1) y = (yy >= 0) ? x * seluScale : x * (yy + seluScale * seluAlpha);
+        if (G == 2) y = (yy >= 0) ? 0 : x * (yy + seluScale * seluAlpha);
+    }
+    if (A == 8) {
+        if (G == 0) y = (x > expRange) ? x : log_(exp_(x) + one);
+        if (G == 1) y = x * (one - exp_(-yy));
+        if (G == 2) { const S c = exp_(-yy); y = x * c * (one - c); }
+    }
+    if (A == 9) {
+        if (G == 0) {
+            y = (x < -expRange) ? 0 : x / (exp_(-x) + one);
+        } else {
+            const S c = exp_(xref), d = c + one;
+            if (G == 1) y = (xref > halfExpRange) ? x : x * c * (xref + d) / (d * d);
+            else y = (xref > halfExpRange) ? 0 : x * c * (xref * (two - d) + two * d) / (d * d * d);
+            yref = (xref < -expRange) ? 0 : xref / (exp_(-xref) + one) * gain;
+        }
+    }
+    y *= gain * dy;
+    if (clamp >= 0) {
+        if (G == 0) y = (y > -clamp & y < clamp) ? y : (y >= 0) ? clamp : -clamp;
+        else y = (yref > -clamp & yref < clamp) ? y : 0;
+    }
+    return y;
+}
+
+// bias index of flat element e; 32-bit division whenever the tensor allows it
+__device__ __forceinline__ long long bias_index(long long e, const BiasActArgs& p, bool small) {
+    if (small) return (long long)(((unsigned)e / (unsigned)p.step_b) % (unsigned)p.size_b);
+    return (e / p.step_b) % p.size_b;
+}
+
+template <typename T> struct Vec;
+template <> struct Vec<float> { static constexpr int N = 4; using type = float4; };
+template <> struct Vec<__half> { static constexpr int N = 8; using type = uint4; };
+template <> struct Vec<double> { static constexpr int N = 2; using type = double2; };
+
+template <typename T> __device__ __forceinline__ typename Acc<T>::type to_acc(T v) { return (typename Acc<T>::type)v; }
+template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return __half2float(v); }
+template <typename T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return (T)v; }
+template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half(v); }
+
+// Vectorised kernel: every thread handles whole 16-byte vectors; the tail (size_x % N) is scalar.
+template <typename T, int A, int UNROLL>
+__global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
+    using S = typename Acc<T>::type;
+    using V = typename Vec<T>::type;
+    constexpr int N = Vec<T>::N;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const int G = p.grad;
+    const T* x = (const T*)p.x;
+    const T* b = (const T*)p.b;
+    const T* xref = (const T*)p.xref;
+    const T* yref = (const T*)p.yref;
+    const T* dy = (const T*)p.dy;
+    T* y = (T*)p.y;
+    const long long nvec = p.size_x / N;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const bool b_uniform = (b != nullptr) && (p.step_b % N == 0);   // one bias per vector
+    const bool small = p.size_x <= 0x7fffffffll;
+
+    for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
+        V vx[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long v = v0 + u * stride;
+            if (v < nvec) vx[u] = __ldcs(reinterpret_cast<const V*>(x) + v);      // streaming: read once
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long v = v0 + u * stride;
+            if (v >= nvec) continue;
+            const long long e0 = v * N;
+            alignas(16) T ex[N]; alignas(16) T exr[N]; alignas(16) T eyr[N]; alignas(16) T edy[N]; alignas(16) T out[N];
+            *reinterpret_cast<V*>(ex) = vx[u];
+            if (xref) *reinterpret_cast<V*>(exr) = __ldcs(reinterpret_cast<const V*>(xref) + v);
+            if (yref) *reinterpret_cast<V*>(eyr) = __ldcs(reinterpret_cast<const V*>(yref) + v);
+            if (dy) *reinterpret_cast<V*>(edy) = __ldcs(reinterpret_cast<const V*>(dy) + v);
+            S bu = 0;
+            if (b_uniform) bu = to_acc<T>(b[bias_index(e0, p, small)]);
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                S bb = bu;
+                if (b != nullptr && !b_uniform) bb = to_acc<T>(b[bias_index(e0 + j, p, small)]);
+                out[j] = from_acc<T>(eval<S, A>(to_acc<T>(ex[j]), bb, xref ? to_acc<T>(exr[j]) : (S)0,
+                                                yref ? to_acc<T>(eyr[j]) : (S)0, dy ? to_acc<T>(edy[j]) : (S)1, G,
+                                                alpha, gain, clamp));
+            }
+            __stcs(reinterpret_cast<V*>(y) + v, *reinterpret_cast<V*>(out));
+        }
+    }
+    // scalar tail
+    const long long tail0 = nvec * N;
+    for (long long e = tail0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < p.size_x; e += stride) {
+        const S bb = b ? to_acc<T>(b[bias_index(e, p, small)]) : (S)0;
+        y[e] = from_acc<T>(eval<S, A>(to_acc<T>(x[e]), bb, xref ? to_acc<T>(xref[e]) : (S)0,
+                                      yref ? to_acc<T>(yref[e]) : (S)0, dy ? to_acc<T>(dy[e]) : (S)1, G, alpha,
+                                      gain, clamp));
+    }
+}
+
+template <typename T, int A>
+static int launch_bias_act(const BiasActArgs& p, cudaStream_t st) {
+    constexpr int UNROLL = 4;
+    constexpr int N = Vec<T>::N;
+    const long long nvec = p.size_x / N;
+    long long blocks = ceil_div<long long>(nvec > 0 ? nvec : 1, 256ll * UNROLL);
+    const long long cap = (long long)sm_count() * 8;            // 8 resident blocks of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    bias_act_kernel<T, A, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(p);
+    IDE3D_CHECK_LAUNCH("bias_act_kernel");
+    return IDE3D_OK;
+}
+
+template <typename T>
+static int dispatch_act(const BiasActArgs& p, int act, cudaStream_t st) {
+    switch (act) {
+        case 1: return launch_bias_act<T, 1>(p, st);
+        case 2: return launch_bias_act<T, 2>(p, st);
+        case 3: return launch_bias_act<T, 3>(p, st);
+        case 4: return launch_bias_act<T, 4>(p, st);
+        case 5: return launch_bias_act<T, 5>(p, st);
+        case 6: return launch_bias_act<T, 6>(p, st);
+        case 7: return launch_bias_act<T, 7>(p, st);
+        case 8: return launch_bias_act<T, 8>(p, st);
+        case 9: return launch_bias_act<T, 9>(p, st);
+    }
+    IDE3D_FAIL(IDE3D_INVALID, "bias_act: unknown activation index %d", act);
+}
+
+}  // namespace ide3d
+
+using namespace ide3d;
+
+extern "C" int ide3d_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy,
+                              void* y, int dtype, int grad, int act, float alpha, float gain, float clamp,
+                              int64_t size_x, int64_t size_b, int64_t step_b, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(size_x >= 0, "bias_act: negative size");
+    if (size_x == 0) return IDE3D_OK;
+    IDE3D_REQUIRE(x && y, "bias_act: null x/y");
+    IDE3D_REQUIRE(grad >= 0 && grad <= 2, "bias_act: grad must be 0, 1 or 2");
+    IDE3D_REQUIRE(b == nullptr || (size_b > 0 && step_b > 0), "bias_act: bad bias geometry");
+    const uintptr_t all = (uintptr_t)x | (uintptr_t)y | (uintptr_t)xref | (uintptr_t)yref | (uintptr_t)dy;
+    IDE3D_REQUIRE((all & 15) == 0, "bias_act: tensors must be 16-byte aligned");
+    BiasActArgs p{x, b, xref, yref, dy, y, grad, alpha, gain, clamp, size_x, size_b > 0 ? size_b : 1,
+                  step_b > 0 ? step_b : 1};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case IDE3D_F32: return dispatch_act<float>(p, act, st);
+        case IDE3D_F16: return dispatch_act<__half>(p, act, st);
+        case IDE3D_F64: return dispatch_act<double>(p, act, st);
+    }
+    IDE3D_FAIL(IDE3D_INVALID, "bias_act: unsupported dtype %d", dtype);
+}

@@ -1,0 +1,287 @@
+// upfirdn2d for sm_100a: pad -> zero-upsample -> FIR -> decimate.
+// Replaces upfirdn2d_kernel_small/_large (torch_utils/ops/upfirdn2d.cu:29-200) behind the field set of
+// upfirdn2d_kernel_params (upfirdn2d.h:14-40).
+//
+//   y[oy,ox] = gain * sum_{ky,kx} F[ky,kx] * X[(oy*dy + ky - py0)/uy, (ox*dx + kx - px0)/ux]
+//   over taps whose numerators are >= 0, divisible by the up factor and inside the image;
+//   F = f flipped unless `flip` (true convolution by default).
+//
+// HBM roofline: (numel_in + numel_out) * sizeof(T).  Two kernels:
+//   * patch kernel (W-contiguous tensors, the StyleGAN2/3 filter shapes): a 64x64 output tile per block,
+//     input tile staged once in shared memory (out-of-image = 0), each thread produces a 4x4 output patch
+//     from a register window.  Polyphase structure is resolved at COMPILE time: the phase of the
+//     padding (pad mod up) is a template parameter, so every tap -> window index is a constant and there
+//     are no divisions, no bounds checks and no wasted zero taps in the inner loop.
+//   * generic kernel: any strides (channels_last included), any filter, one thread per output.
+#include "common.cuh"
+
+namespace ide3d {
+
+struct UpfirArgs {
+    const void* x;
+    const float* f;
+    void* y;
+    int ux, uy, dx, dy, px0, py0, flip;
+    float gain;
+    int in_w, in_h, in_c, in_n;
+    long long isw, ish, isc, isn;
+    int fw, fh;
+    long long fsw, fsh;
+    int out_w, out_h;
+    long long osw, osh, osc, osn;
+};
+
+template <typename T> struct AccT { using type = float; };
+template <> struct AccT<double> { using type = double; };
+template <typename T> __device__ __forceinline__ typename AccT<T>::type ld(const T* p) { return (typename AccT<T>::type)(*p); }
+template <> __device__ __forceinline__ float ld<__half>(const __half* p) { return __half2float(*p); }
+template <typename T> __device__ __forceinline__ void st(T* p, typename AccT<T>::type v) { *p = (T)v; }
+template <> __device__ __forceinline__ void st<__half>(__half* p, float v) { *p = __float2half(v); }
+
+// ------------------------------------------------------------------------------------------
+// compile-time polyphase bookkeeping for one axis: U = up, D = down, F = taps, PH = pad0 mod U
+constexpr int cmod(int a, int m) { return ((a % m) + m) % m; }
+constexpr int cfloor(int a, int m) { return (a - cmod(a, m)) / m; }
+constexpr int kPatch = 4;                                   // outputs per thread per axis
+constexpr int kTile = 64;                                   // outputs per block per axis
+
+template <int U, int D, int F, int PH>
+struct Axis {
+    // output j of a patch whose origin is a multiple of kPatch
+    static constexpr int k0(int j) { return cmod(PH - j * D, U); }                       // first live tap
+    static constexpr int taps(int j) { return k0(j) < F ? (F - k0(j) + U - 1) / U : 0; }
+    static constexpr int off(int j) { return cfloor(j * D - PH + k0(j), U); }            // input index of that tap (minus runtime base)
+    static constexpr int lo() {
+        int m = 1 << 20;
+        for (int j = 0; j < kPatch; ++j) if (taps(j) > 0 && off(j) < m) m = off(j);
+        return m == (1 << 20) ? 0 : m;
+    }
+    static constexpr int hi() {
+        int m = -(1 << 20);
+        for (int j = 0; j < kPatch; ++j) if (taps(j) > 0 && off(j) + taps(j) - 1 > m) m = off(j) + taps(j) - 1;
+        return m == -(1 << 20) ? 0 : m;
+    }
+    static constexpr int kWin = hi() - lo() + 1;                                         // window length per patch
+    static constexpr int kStep = kPatch * D / U;                                         // window advance per patch
+    static constexpr int kTileIn = (kTile / kPatch - 1) * kStep + kWin;                  // staged inputs per tile
+    static_assert((kPatch * D) % U == 0, "patch origin must stay phase aligned");
+};
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+__global__ void __launch_bounds__(256) upfirdn2d_patch_kernel(const UpfirArgs p, int tiles_x, int tiles_y) {
+    using S = typename AccT<T>::type;
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    constexpr int TIW = AX::kTileIn, TIH = AY::kTileIn;
+    constexpr int TIWP = TIW | 1;                            // odd row pitch: spreads rows over banks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    S* tile = reinterpret_cast<S*>(smem_raw);
+
+    // filter taps to registers, flipped here once
+    S fk[FH][FW];
+#pragma unroll
+    for (int ky = 0; ky < FH; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < FW; ++kx) {
+            const int sy = p.flip ? ky : FH - 1 - ky, sx = p.flip ? kx : FW - 1 - kx;
+            fk[ky][kx] = (S)p.f[sy * p.fsh + sx * p.fsw] * (S)p.gain;
+        }
+
+    const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);      // pad = U*a + PH
+    const long long tiles_plane = (long long)tiles_x * tiles_y;
+    const long long total = tiles_plane * p.in_c * p.in_n;
+
+    for (long long blk = blockIdx.x; blk < total; blk += gridDim.x) {
+        const long long plane = blk / tiles_plane;
+        const int t = (int)(blk - plane * tiles_plane);
+        const int n = (int)(plane / p.in_c), c = (int)(plane - (long long)n * p.in_c);
+        const int ox_t = (t % tiles_x) * kTile, oy_t = (t / tiles_x) * kTile;
+        const int ix_t = ox_t * DX / UX - ax + AX::lo();
+        const int iy_t = oy_t * DY / UY - ay + AY::lo();
+        const T* xin = (const T*)p.x + n * p.isn + c * p.isc;
+
+        __syncthreads();                                      // previous tile fully consumed
+        for (int i = threadIdx.x; i < TIW * TIH; i += 256) {
+            const int ty = i / TIW, tx = i - ty * TIW;
+            const int gx = ix_t + tx, gy = iy_t + ty;
+            S v = 0;
+            if ((unsigned)gx < (unsigned)p.in_w && (unsigned)gy < (unsigned)p.in_h) v = ld<T>(xin + gy * p.ish + gx);
+            tile[ty * TIWP + tx] = v;
+        }
+        __syncthreads();
+
+        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+        const S* wbase = tile + (ty * AY::kStep) * TIWP + tx * AX::kStep;
+        S acc[kPatch][kPatch];
+#pragma unroll
+        for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+            for (int j = 0; j < kPatch; ++j) acc[i][j] = 0;
+
+#pragma unroll
+        for (int r = 0; r < AY::kWin; ++r) {
+            S win[AX::kWin];
+#pragma unroll
+            for (int q = 0; q < AX::kWin; ++q) win[q] = wbase[r * TIWP + q];
+#pragma unroll
+            for (int i = 0; i < kPatch; ++i) {
+#pragma unroll
+                for (int ty_ = 0; ty_ < AY::taps(i); ++ty_) {
+                    if (AY::off(i) - AY::lo() + ty_ != r) continue;              // folded at compile time
+                    const int ky = AY::k0(i) + ty_ * UY;
+#pragma unroll
+                    for (int j = 0; j < kPatch; ++j)
+#pragma unroll
+                        for (int tx_ = 0; tx_ < AX::taps(j); ++tx_)
+                            acc[i][j] += fk[ky][AX::k0(j) + tx_ * UX] * win[AX::off(j) - AX::lo() + tx_];
+                }
+            }
+        }
+
+        const int ox0 = ox_t + tx * kPatch, oy0 = oy_t + ty * kPatch;
+        T* yout = (T*)p.y + n * p.osn + c * p.osc;
+#pragma unroll
+        for (int i = 0; i < kPatch; ++i) {
+            const int oy = oy0 + i;
+            if (oy >= p.out_h) break;
+            T* rowp = yout + oy * p.osh + ox0;
+            if (sizeof(T) == 4 && ox0 + kPatch <= p.out_w && ((reinterpret_cast<uintptr_t>(rowp) & 15) == 0)) {
+                __stcs(reinterpret_cast<float4*>(rowp), make_float4((float)acc[i][0], (float)acc[i][1], (float)acc[i][2], (float)acc[i][3]));
+            } else {
+#pragma unroll
+                for (int j = 0; j < kPatch; ++j)
+                    if (ox0 + j < p.out_w) st<T>(rowp + j, acc[i][j]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic: any strides / filter / factors.  Thread order follows the fastest-varying output stride.
+template <typename T>
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(const UpfirArgs p, int c_fastest) {
+    using S = typename AccT<T>::type;
+    const long long total = (long long)p.out_w * p.out_h * p.in_c * p.in_n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int ox, oy, c, n;
+        long long r = i;
+        if (c_fastest) { c = (int)(r % p.in_c); r /= p.in_c; ox = (int)(r % p.out_w); r /= p.out_w; oy = (int)(r % p.out_h); n = (int)(r / p.out_h); }
+        else { ox = (int)(r % p.out_w); r /= p.out_w; oy = (int)(r % p.out_h); r /= p.out_h; c = (int)(r % p.in_c); n = (int)(r / p.in_c); }
+        const int bx = ox * p.dx - p.px0, by = oy * p.dy - p.py0;
+        const int kx0 = ((-bx) % p.ux + p.ux) % p.ux, ky0 = ((-by) % p.uy + p.uy) % p.uy;
+        const T* xin = (const T*)p.x + n * p.isn + c * p.isc;
+        S acc = 0;
+        for (int ky = ky0; ky < p.fh; ky += p.uy) {
+            const int iy = (by + ky) / p.uy;                    // exact
+            if (iy < 0 || by + ky < 0) continue;
+            if (iy >= p.in_h) break;
+            const int sy = p.flip ? ky : p.fh - 1 - ky;
+            for (int kx = kx0; kx < p.fw; kx += p.ux) {
+                const int ix = (bx + kx) / p.ux;
+                if (ix < 0 || bx + kx < 0) continue;
+                if (ix >= p.in_w) break;
+                const int sx = p.flip ? kx : p.fw - 1 - kx;
+                acc += (S)p.f[sy * p.fsh + sx * p.fsw] * ld<T>(xin + iy * p.ish + ix * p.isw);
+            }
+        }
+        st<T>((T*)p.y + n * p.osn + c * p.osc + oy * p.osh + ox * p.osw, acc * (S)p.gain);
+    }
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+static int launch_patch(const UpfirArgs& p, cudaStream_t st_) {
+    using S = typename AccT<T>::type;
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    const size_t smem = (size_t)(AX::kTileIn | 1) * AY::kTileIn * sizeof(S);
+    auto kern = upfirdn2d_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    if (smem > 48 * 1024) IDE3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = ceil_div(p.out_w, kTile), tiles_y = ceil_div(p.out_h, kTile);
+    const long long total = (long long)tiles_x * tiles_y * p.in_c * p.in_n;
+    int per_sm = 1;
+    IDE3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, 256, smem, st_>>>(p, tiles_x, tiles_y);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_patch_kernel");
+    return IDE3D_OK;
+}
+
+// phase dispatch: PHX in [0,UX), PHY in [0,UY)
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH>
+static int dispatch_phase(const UpfirArgs& p, cudaStream_t s) {
+    const int phx = p.px0 - floor_div(p.px0, UX) * UX, phy = p.py0 - floor_div(p.py0, UY) * UY;
+    if constexpr (UX == 1 && UY == 1) return launch_patch<T, UX, UY, DX, DY, FW, FH, 0, 0>(p, s);
+    if constexpr (UX == 2 && UY == 1) return phx ? launch_patch<T, UX, UY, DX, DY, FW, FH, 1, 0>(p, s) : launch_patch<T, UX, UY, DX, DY, FW, FH, 0, 0>(p, s);
+    if constexpr (UX == 1 && UY == 2) return phy ? launch_patch<T, UX, UY, DX, DY, FW, FH, 0, 1>(p, s) : launch_patch<T, UX, UY, DX, DY, FW, FH, 0, 0>(p, s);
+    if constexpr (UX == 2 && UY == 2) {
+        if (phx == 0 && phy == 0) return launch_patch<T, 2, 2, DX, DY, FW, FH, 0, 0>(p, s);
+        if (phx == 1 && phy == 0) return launch_patch<T, 2, 2, DX, DY, FW, FH, 1, 0>(p, s);
+        if (phx == 0 && phy == 1) return launch_patch<T, 2, 2, DX, DY, FW, FH, 0, 1>(p, s);
+        return launch_patch<T, 2, 2, DX, DY, FW, FH, 1, 1>(p, s);
+    }
+    IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: no phase table");
+}
+
+template <typename T>
+static int launch_generic(const UpfirArgs& p, cudaStream_t s) {
+    const long long total = (long long)p.out_w * p.out_h * p.in_c * p.in_n;
+    long long grid = ceil_div<long long>(total, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    const int c_fastest = (p.osc == 1 && p.osw != 1) ? 1 : 0;
+    upfirdn2d_generic_kernel<T><<<(unsigned)grid, 256, 0, s>>>(p, c_fastest);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_generic_kernel");
+    return IDE3D_OK;
+}
+
+template <typename T>
+static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
+    const bool wcontig = (p.isw == 1 && p.osw == 1);
+    if (wcontig && sizeof(T) <= 4) {
+#define IDE3D_CASE(UX, UY, DX, DY, FW, FH)                                                              \
+    if (p.ux == UX && p.uy == UY && p.dx == DX && p.dy == DY && p.fw == FW && p.fh == FH)                \
+        return dispatch_phase<T, UX, UY, DX, DY, FW, FH>(p, s);
+        IDE3D_CASE(1, 1, 1, 1, 4, 4)      // conv-up post filter (conv2d_resample.py:125)
+        IDE3D_CASE(2, 2, 1, 1, 4, 4)      // upsample2d of the skip image (networks.py:841)
+        IDE3D_CASE(1, 1, 2, 2, 4, 4)      // downsample2d
+        IDE3D_CASE(2, 1, 1, 1, 12, 1)     // separable 12-tap passes (StyleGAN3 filters, filtered_lrelu fallback)
+        IDE3D_CASE(1, 2, 1, 1, 1, 12)
+        IDE3D_CASE(1, 1, 2, 1, 12, 1)
+        IDE3D_CASE(1, 1, 1, 2, 1, 12)
+        IDE3D_CASE(1, 1, 1, 1, 12, 1)
+        IDE3D_CASE(1, 1, 1, 1, 1, 12)
+#undef IDE3D_CASE
+    }
+    return launch_generic<T>(p, s);
+}
+
+}  // namespace ide3d
+
+using namespace ide3d;
+
+extern "C" int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* q, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(q != nullptr, "upfirdn2d: null params");
+    IDE3D_REQUIRE(q->x && q->f && q->y, "upfirdn2d: null tensor");
+    IDE3D_REQUIRE(q->up_x >= 1 && q->up_y >= 1 && q->down_x >= 1 && q->down_y >= 1, "upsampling and downsampling factors must be at least 1");
+    IDE3D_REQUIRE(q->f_w >= 1 && q->f_h >= 1, "f must be at least 1x1");
+    IDE3D_REQUIRE(q->in_w > 0 && q->in_h > 0 && q->in_c > 0 && q->in_n > 0, "x is empty");
+    IDE3D_REQUIRE(q->out_w >= 1 && q->out_h >= 1, "output must be at least 1x1");
+    UpfirArgs p;
+    p.x = q->x; p.f = q->f; p.y = q->y;
+    p.ux = q->up_x; p.uy = q->up_y; p.dx = q->down_x; p.dy = q->down_y; p.px0 = q->pad_x0; p.py0 = q->pad_y0;
+    p.flip = q->flip; p.gain = q->gain;
+    p.in_w = q->in_w; p.in_h = q->in_h; p.in_c = q->in_c; p.in_n = q->in_n;
+    p.isw = q->in_stride_w; p.ish = q->in_stride_h; p.isc = q->in_stride_c; p.isn = q->in_stride_n;
+    p.fw = q->f_w; p.fh = q->f_h; p.fsw = q->f_stride_w; p.fsh = q->f_stride_h;
+    p.out_w = q->out_w; p.out_h = q->out_h;
+    p.osw = q->out_stride_w; p.osh = q->out_stride_h; p.osc = q->out_stride_c; p.osn = q->out_stride_n;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (q->dtype) {
+        case IDE3D_F32: return dispatch_upfirdn2d<float>(p, s);
+        case IDE3D_F16: return dispatch_upfirdn2d<__half>(p, s);
+        case IDE3D_F64: return dispatch_upfirdn2d<double>(p, s);
+    }
+    IDE3D_FAIL(IDE3D_INVALID, "upfirdn2d: unsupported dtype %d", q->dtype);
+}

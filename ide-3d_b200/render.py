@@ -1,0 +1,135 @@
+"""Functional front-end of the fused renderer kernels (ide3d_raymarch_fwd / ide3d_sample_voxel / ide3d_sigma_grid).
+
+Everything takes CUDA tensors and raises otherwise.  The decoder is passed as a list of heads
+``(in_sel, out_offset, w1 [hid,in], b1 [hid], w2 [out,hid], b2 [out])`` with in_sel 0 = texture features,
+1 = shape features, 2 = both (64 inputs) -- the ide3d_decoder of include/ide3d_b200.h.
+"""
+
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+N_FEAT, N_SEG, N_OUT = 32, 19, 52
+
+
+class PackedDecoder:
+    """fp32 device copies of the head parameters plus the C struct that points at them (kept alive together)."""
+
+    def __init__(self, heads, device):
+        assert 1 <= len(heads) <= 4
+        self.tensors = []
+        self.struct = L.Decoder()
+        self.struct.num_heads = len(heads)
+        for i, (in_sel, out_off, w1, b1, w2, b2) in enumerate(heads):
+            ts = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t in (w1, b1, w2, b2)]
+            n_in = N_FEAT * (2 if in_sel == 2 else 1)
+            if ts[0].shape[1] != n_in or ts[2].shape[1] != ts[0].shape[0] or ts[1].numel() != ts[0].shape[0] \
+                    or ts[3].numel() != ts[2].shape[0]:
+                raise RuntimeError('ide3d_b200: inconsistent decoder head shapes')
+            self.tensors += ts
+            self.struct.heads[i] = L.MlpHead(int(in_sel), ts[0].shape[0], int(out_off), ts[2].shape[0],
+                                             *[t.data_ptr() for t in ts])
+
+
+def dense_heads(w1, b1, w2, b2):
+    """A dense [hid,64] / [52,hid] decoder as a single head."""
+    return [(2, 0, w1, b1, w2, b2)]
+
+
+def as_planes(t):
+    """float32 channels-last view of a tri-plane tensor [N,96,H,W] (one ide3d_planes_to_nhwc pass if needed)."""
+    L.require_cuda(t)
+    if t.dtype != torch.float32:
+        t = t.float()
+    if t.stride(1) == 1 and t.is_contiguous(memory_format=torch.channels_last):
+        return t
+    n, c, h, w = t.shape
+    out = torch.empty([n, c, h, w], dtype=torch.float32, device=t.device, memory_format=torch.channels_last)
+    s = t.stride()
+    L.check(L.get_lib().ide3d_planes_to_nhwc(L.ptr(t), n, c, h, w, s[0], s[1], s[2], s[3], L.ptr(out), L.stream_ptr(t.device)))
+    return out
+
+
+def _decoder(dec, device):
+    return dec if isinstance(dec, PackedDecoder) else PackedDecoder(dec, device)
+
+
+def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, fov=18.0, ray_start=2.25,
+             ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
+             clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None,
+             return_weights=False, convert_layout=True):
+    """Fused render of N frames.  -> feat [N,R,51], depth [N,R,1], weights [N,R,S,1] | None.
+    jitter_u: explicit uniforms [N,R,S]; jitter_seed: in-kernel counter hash; neither: no jitter."""
+    if clamp_mode not in ('softplus', 'relu'):
+        raise ValueError('Need to choose clamp mode')
+    if fill_mode not in (None, 'weight'):
+        raise NotImplementedError(f'fill_mode={fill_mode!r} is not supported by the fused renderer')
+    L.require_cuda(planes_tex, planes_seg, cam2world)
+    tex = as_planes(planes_tex) if convert_layout else planes_tex
+    seg = as_planes(planes_seg) if convert_layout else planes_seg
+    dev = tex.device
+    n = tex.shape[0]
+    W, H = (resolution, resolution) if isinstance(resolution, int) else resolution
+    R, S = W * H, int(num_steps)
+    cam = cam2world.to(device=dev, dtype=torch.float32).reshape(n, 16).contiguous()
+    dec = _decoder(decoder, dev)
+    feat = torch.empty([n, R, N_OUT - 1], dtype=torch.float32, device=dev)
+    depth = torch.empty([n, R, 1], dtype=torch.float32, device=dev)
+    weights = torch.empty([n, R, S, 1], dtype=torch.float32, device=dev) if return_weights else None
+    p = L.RaymarchParams()
+    p.tex, p.seg, p.dec = L.triplane_view(tex), L.triplane_view(seg), dec.struct
+    p.cam2world = L.ptr(cam)
+    p.n, p.res_w, p.res_h, p.num_steps = n, W, H, S
+    p.fov_deg, p.ray_start, p.ray_end, p.box_scale = float(fov), float(ray_start), float(ray_end), float(box_scale)
+    if jitter_u is not None:
+        jitter_u = jitter_u.to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous()
+        p.jitter_mode, p.jitter_u = L.JITTER_TENSOR, L.ptr(jitter_u)
+    elif jitter_seed is not None:
+        p.jitter_mode, p.jitter_seed = L.JITTER_HASH, int(jitter_seed) & 0xFFFFFFFFFFFFFFFF
+    else:
+        p.jitter_mode = L.JITTER_NONE
+    if noise is not None and noise_std:
+        noise = noise.to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous()
+        p.noise, p.noise_std = L.ptr(noise), float(noise_std)
+    p.clamp_mode = L.CLAMP_SOFTPLUS if clamp_mode == 'softplus' else L.CLAMP_RELU
+    p.last_back, p.white_back = int(bool(last_back)), int(bool(white_back))
+    p.max_depth, p.fill_weight = float(max_depth or 0.0), int(fill_mode == 'weight')
+    p.out_feat, p.out_depth, p.out_weights = L.ptr(feat), L.ptr(depth), L.ptr(weights)
+    with torch.cuda.device(dev):
+        L.check(L.get_lib().ide3d_raymarch_fwd(C.byref(p), L.stream_ptr(dev)))
+    return feat, depth, weights
+
+
+def sample_voxel(planes_tex, planes_seg, decoder, points, box_scale=2.0, sigma_only=False):
+    """Decode world-space points [N,P,3] -> [N,P,52] (or [N,P,1] sigma)."""
+    tex, seg = as_planes(planes_tex), as_planes(planes_seg)
+    dev = tex.device
+    pts = points.to(device=dev, dtype=torch.float32).contiguous()
+    n, P = pts.shape[0], pts.shape[1]
+    dec = _decoder(decoder, dev)
+    out = torch.empty([n, P, 1 if sigma_only else N_OUT], dtype=torch.float32, device=dev)
+    tv, sv = L.triplane_view(tex), L.triplane_view(seg)
+    with torch.cuda.device(dev):
+        L.check(L.get_lib().ide3d_sample_voxel(C.byref(tv), C.byref(sv), C.byref(dec.struct), L.ptr(pts), P,
+                                               float(box_scale), int(sigma_only), L.ptr(out), L.stream_ptr(dev)))
+    return out
+
+
+def sigma_grid(planes_tex, planes_seg, decoder, grid_n=256, voxel_origin=(0, 0, 0), cube_length=2.0, pre_scale=0.9,
+               box_scale=2.0, first=0, count=None):
+    """Density for flat voxel indices [first, first+count) of the grid 0.9*create_samples(grid_n, origin, cube)
+    (extract_shapes.py:74-103), points generated in the kernel.  -> [N, count]."""
+    tex, seg = as_planes(planes_tex), as_planes(planes_seg)
+    dev = tex.device
+    count = grid_n ** 3 - first if count is None else count
+    dec = _decoder(decoder, dev)
+    out = torch.empty([tex.shape[0], count], dtype=torch.float32, device=dev)
+    tv, sv = L.triplane_view(tex), L.triplane_view(seg)
+    org = (C.c_float * 3)(*[float(v) for v in voxel_origin])
+    with torch.cuda.device(dev):
+        L.check(L.get_lib().ide3d_sigma_grid(C.byref(tv), C.byref(sv), C.byref(dec.struct), int(grid_n), C.byref(org),
+                                             float(cube_length), float(pre_scale), float(box_scale), int(first),
+                                             int(count), L.ptr(out), L.stream_ptr(dev)))
+    return out

@@ -1,0 +1,105 @@
+"""Fused bias + activation (+ gain, clamp) on sm_100a.
+
+Same public surface as the reference's torch_utils/ops/bias_act.py: `activation_funcs` (:21-31) and
+`bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda')` (:52).
+Compute goes through `bias_act_plugin.bias_act` -> ide3d_bias_act (csrc/bias_act.cu).  There is no
+PyTorch fallback in this package: CPU tensors and impl='ref' raise (the CPU restatement is oracle/ops.py,
+test infrastructure only).
+"""
+
+import math
+
+import torch
+
+from .. import custom_ops
+
+
+class _Spec(dict):
+    __getattr__ = dict.__getitem__
+
+
+def _spec(def_alpha, def_gain, cuda_idx, ref, has_2nd_grad):
+    return _Spec(def_alpha=def_alpha, def_gain=def_gain, cuda_idx=cuda_idx, ref=ref, has_2nd_grad=has_2nd_grad)
+
+
+_SQRT2 = math.sqrt(2)
+activation_funcs = {
+    'linear':   _spec(0,   1,      1, '',  False),
+    'relu':     _spec(0,   _SQRT2, 2, 'y', False),
+    'lrelu':    _spec(0.2, _SQRT2, 3, 'y', False),
+    'tanh':     _spec(0,   1,      4, 'y', True),
+    'sigmoid':  _spec(0,   1,      5, 'y', True),
+    'elu':      _spec(0,   1,      6, 'y', True),
+    'selu':     _spec(0,   1,      7, 'y', True),
+    'softplus': _spec(0,   1,      8, 'y', True),
+    'swish':    _spec(0,   _SQRT2, 9, 'x', True),
+}
+
+_plugin = None
+
+
+def _init():
+    global _plugin
+    if _plugin is None:
+        _plugin = custom_ops.get_plugin(module_name='bias_act_plugin', sources=['bias_act.cu'])
+    return True
+
+
+def _layout(x):
+    """Tensor in a dense layout the kernel accepts (contiguous or channels_last), like bias_act.py:145-146."""
+    if x.ndim == 4 and x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    return x.contiguous()
+
+
+class _BiasAct(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, b, dim, spec, alpha, gain, clamp):
+        x = _layout(x)
+        y = _plugin.bias_act(x, b, None, None, None, 0, dim, spec.cuda_idx, alpha, gain, clamp)
+        ctx.cfg = (dim, spec, alpha, gain, clamp)
+        ctx.has_bias = b is not None
+        ctx.cl = (x.ndim == 4 and not x.is_contiguous())
+        ctx.save_for_backward(x if 'x' in spec.ref or spec.has_2nd_grad else None, b if b is not None else None,
+                              y if 'y' in spec.ref else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dim, spec, alpha, gain, clamp = ctx.cfg
+        x, b, y = ctx.saved_tensors
+        dx = db = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            dy = dy.contiguous(memory_format=torch.channels_last) if ctx.cl else dy.contiguous()
+            dx = dy
+            if spec.cuda_idx != 1 or gain != 1 or clamp >= 0:
+                dx = _plugin.bias_act(dy, b, x, y, None, 1, dim, spec.cuda_idx, alpha, gain, clamp)
+        if ctx.needs_input_grad[1] and ctx.has_bias:
+            db = dx.sum([i for i in range(dx.ndim) if i != dim])
+        return dx, db, None, None, None, None, None
+
+
+def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
+    """y = clamp(gain * act(x + b)).  Arguments as in the reference (bias_act.py:52-86)."""
+    assert isinstance(x, torch.Tensor)
+    assert impl in ['ref', 'cuda']
+    if impl == 'ref':
+        raise NotImplementedError("ide3d_b200 has no PyTorch reference path; impl='ref' lives in oracle/ops.py (tests only)")
+    if x.device.type != 'cuda':
+        raise RuntimeError('ide3d_b200.bias_act: x must be a CUDA tensor (no CPU path in this package)')
+    _init()
+    assert clamp is None or clamp >= 0
+    spec = activation_funcs[act]
+    alpha = float(alpha if alpha is not None else spec.def_alpha)
+    gain = float(gain if gain is not None else spec.def_gain)
+    clamp = float(clamp if clamp is not None else -1)
+    if b is not None:
+        assert isinstance(b, torch.Tensor) and b.ndim == 1
+        assert 0 <= dim < x.ndim
+        assert b.shape[0] == x.shape[dim]
+    # identity short-cut of the reference (bias_act.py:149)
+    if act == 'linear' and gain == 1 and clamp < 0 and b is None:
+        return x
+    if torch.is_grad_enabled() and (x.requires_grad or (b is not None and b.requires_grad)):
+        return _BiasAct.apply(x, b, dim, spec, alpha, gain, clamp)
+    return _plugin.bias_act(_layout(x), b, None, None, None, 0, dim, spec.cuda_idx, alpha, gain, clamp)

@@ -1,0 +1,273 @@
+"""StyleGAN2 building blocks of the tri-plane backbone and the super-resolution head.
+
+The IDE-3D release does not contain its generator source (it travels inside the checkpoint pickle);
+the nearest in-repo definitions are in inversion/networks.py (modulated_conv2d :55-130, FullyConnectedLayer
+:136-165, MappingNetwork :243-325, SynthesisLayer :330-514, ToRGBLayer :670-713, SegSynthesisBlock :966-1139).
+The classes below restate those layers for inference: same parameter names/shapes/initialisation and the same
+arithmetic, with the StyleNeRF-only options (pixelshuffle / liif / 3-D modes, magnitude EMA, ...) left out.
+Every convolution goes to cuDNN (conv2d_resample -> conv2d_gradfix); the surrounding ops are this package's
+sm_100a kernels: upfirdn2d (FIR after the transposed conv, skip-image upsampling) and bias_act.
+"""
+
+import numpy as np
+import torch
+
+from ..torch_utils import misc, persistence
+from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
+
+
+def normalize_2nd_moment(x, dim=1, eps=1e-8):
+    return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
+
+
+def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
+                     flip_weight=True, fused_modconv=True):
+    """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I]."""
+    batch_size = x.shape[0]
+    out_channels, in_channels, kh, kw = weight.shape
+    if x.dtype == torch.float16 and demodulate:      # keep fp16 in range (:78-81)
+        weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
+        styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
+    w = dcoefs = None
+    if demodulate or fused_modconv:
+        w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)            # [N,O,I,k,k]
+    if demodulate:
+        dcoefs = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()                       # [N,O]
+    if demodulate and fused_modconv:
+        w = w * dcoefs.reshape(batch_size, -1, 1, 1, 1)
+
+    if not fused_modconv:                           # scale activations instead of weights (:97-111)
+        x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
+        x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
+                                            padding=padding, flip_weight=flip_weight)
+        if demodulate and noise is not None:
+            x = fma.fma(x, dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1), noise.to(x.dtype))
+        elif demodulate:
+            x = x * dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1)
+        elif noise is not None:
+            x = x.add_(noise.to(x.dtype))
+        return x
+
+    # one grouped convolution for the whole batch (:113-129)
+    x = x.reshape(1, -1, *x.shape[2:])
+    w = w.reshape(-1, in_channels, kh, kw)
+    x = conv2d_resample.conv2d_resample(x=x, w=w.to(x.dtype), f=resample_filter, up=up, down=down, padding=padding,
+                                        groups=batch_size, flip_weight=flip_weight)
+    x = x.reshape(batch_size, -1, *x.shape[2:])
+    if noise is not None:
+        x = x.add_(noise)
+    return x
+
+
+@persistence.persistent_class
+class FullyConnectedLayer(torch.nn.Module):
+    """inversion/networks.py:136-165: weight ~ N(0,1)/lr_mult, runtime gain lr_mult/sqrt(in)."""
+
+    def __init__(self, in_features, out_features, bias=True, activation='linear', lr_multiplier=1, bias_init=0):
+        super().__init__()
+        self.in_features, self.out_features, self.activation = in_features, out_features, activation
+        self.weight = torch.nn.Parameter(torch.randn([out_features, in_features]) / lr_multiplier)
+        self.bias = torch.nn.Parameter(torch.full([out_features], np.float32(bias_init))) if bias else None
+        self.weight_gain = lr_multiplier / np.sqrt(in_features)
+        self.bias_gain = lr_multiplier
+
+    def effective(self):
+        """(W, b) with the runtime gains folded in -- what the fused renderer kernel consumes."""
+        w = self.weight.to(torch.float32) * self.weight_gain
+        b = None if self.bias is None else self.bias.to(torch.float32) * self.bias_gain
+        return w, b
+
+    def forward(self, x):
+        w = self.weight.to(x.dtype) * self.weight_gain
+        b = self.bias
+        if b is not None:
+            b = b.to(x.dtype)
+            if self.bias_gain != 1:
+                b = b * self.bias_gain
+        if self.activation == 'linear' and b is not None:
+            return torch.addmm(b.unsqueeze(0), x, w.t())
+        x = x.matmul(w.t())
+        return bias_act.bias_act(x, b, act=self.activation)
+
+
+@persistence.persistent_class
+class MappingNetwork(torch.nn.Module):
+    """z (+ camera label c) -> ws [N, num_ws, w_dim]; inversion/networks.py:243-325."""
+
+    def __init__(self, z_dim, c_dim, w_dim, num_ws, num_layers=8, embed_features=None, layer_features=None,
+                 activation='lrelu', lr_multiplier=0.01, w_avg_beta=0.995):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.num_ws = z_dim, c_dim, w_dim, num_ws
+        self.num_layers, self.w_avg_beta = num_layers, w_avg_beta
+        if embed_features is None:
+            embed_features = w_dim
+        if c_dim == 0:
+            embed_features = 0
+        if layer_features is None:
+            layer_features = w_dim
+        feats = [z_dim + embed_features] + [layer_features] * (num_layers - 1) + [w_dim]
+        if c_dim > 0:
+            self.embed = FullyConnectedLayer(c_dim, embed_features)
+        for idx in range(num_layers):
+            setattr(self, f'fc{idx}', FullyConnectedLayer(feats[idx], feats[idx + 1], activation=activation,
+                                                          lr_multiplier=lr_multiplier))
+        if num_ws is not None and w_avg_beta is not None:
+            self.register_buffer('w_avg', torch.zeros([w_dim]))
+
+    def forward(self, z=None, c=None, truncation_psi=1, truncation_cutoff=None, skip_w_avg_update=False, **_unused):
+        x = None
+        if self.z_dim > 0:
+            misc.assert_shape(z, [None, self.z_dim])
+            x = normalize_2nd_moment(z.to(torch.float32))
+        if self.c_dim > 0:
+            misc.assert_shape(c, [None, self.c_dim])
+            y = normalize_2nd_moment(self.embed(c.to(torch.float32)))
+            x = torch.cat([x, y], dim=1) if x is not None else y
+        for idx in range(self.num_layers):
+            x = getattr(self, f'fc{idx}')(x)
+        if self.w_avg_beta is not None and self.training and not skip_w_avg_update:
+            self.w_avg.copy_(x.detach().mean(dim=0).lerp(self.w_avg, self.w_avg_beta))
+        if self.num_ws is not None:
+            x = x.unsqueeze(1).repeat([1, self.num_ws, 1])
+        if truncation_psi != 1:
+            if self.num_ws is None or truncation_cutoff is None:
+                x = self.w_avg.lerp(x, truncation_psi)
+            else:
+                x[:, :truncation_cutoff] = self.w_avg.lerp(x[:, :truncation_cutoff], truncation_psi)
+        return x
+
+
+@persistence.persistent_class
+class SynthesisLayer(torch.nn.Module):
+    """Modulated 3x3 conv (+2x up), noise, bias_act; inversion/networks.py:330-514 ('default' upsampling)."""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, kernel_size=3, up=1, use_noise=True,
+                 activation='lrelu', resample_filter=[1, 3, 3, 1], conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.resolution, self.up, self.use_noise = resolution, up, use_noise
+        self.activation, self.conv_clamp = activation, conv_clamp
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        self.padding = kernel_size // 2
+        self.act_gain = bias_act.activation_funcs[activation].def_gain
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        memory_format = torch.channels_last if channels_last else torch.contiguous_format
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=memory_format))
+        if use_noise:
+            self.register_buffer('noise_const', torch.randn([resolution, resolution]))
+            self.noise_strength = torch.nn.Parameter(torch.zeros([]))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+        assert noise_mode in ['random', 'const', 'none']
+        styles = self.affine(w)
+        noise = None
+        if self.use_noise and noise_mode == 'random':
+            noise = torch.randn([x.shape[0], 1, self.up * x.shape[2], self.up * x.shape[3]], device=x.device) * self.noise_strength
+        if self.use_noise and noise_mode == 'const':
+            noise = self.noise_const * self.noise_strength
+        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
+        act_gain = self.act_gain * gain
+        act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
+
+
+@persistence.persistent_class
+class ToRGBLayer(torch.nn.Module):
+    """Modulated 1x1 conv without demodulation + bias; inversion/networks.py:670-713 (w_dim > 0 branch)."""
+
+    def __init__(self, in_channels, out_channels, w_dim, kernel_size=1, conv_clamp=None, channels_last=False):
+        super().__init__()
+        self.conv_clamp = conv_clamp
+        self.affine = FullyConnectedLayer(w_dim, in_channels, bias_init=1)
+        memory_format = torch.channels_last if channels_last else torch.contiguous_format
+        self.weight = torch.nn.Parameter(torch.randn([out_channels, in_channels, kernel_size, kernel_size]).to(memory_format=memory_format))
+        self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
+        self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
+
+    def forward(self, x, w, fused_modconv=True):
+        styles = self.affine(w) * self.weight_gain
+        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
+        return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+
+
+@persistence.persistent_class
+class SynthesisBlock(torch.nn.Module):
+    """One resolution of a 'skip' StyleGAN2 synthesis network: [conv0(up 2)], conv1, torgb
+    (inversion/networks.py:718-861).  Children order (conv0, conv1, torgb) matters to callers that index the
+    flattened layer list (ide3d-nada/ZSSGAN/model/ZSSGAN_IDE3D.py:425-437)."""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, is_last, resample_filter=[1, 3, 3, 1],
+                 conv_clamp=None, use_fp16=False, fp16_channels_last=False, **layer_kwargs):
+        super().__init__()
+        self.in_channels, self.out_channels, self.w_dim = in_channels, out_channels, w_dim
+        self.resolution, self.img_channels, self.is_last = resolution, img_channels, is_last
+        self.architecture = 'skip'
+        self.use_fp16 = use_fp16
+        self.channels_last = use_fp16 and fp16_channels_last
+        self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
+        self.num_conv = 0
+        self.num_torgb = 0
+        if in_channels == 0:
+            self.const = torch.nn.Parameter(torch.randn([out_channels, resolution, resolution]))
+        if in_channels != 0:
+            self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2,
+                                        resample_filter=resample_filter, conv_clamp=conv_clamp,
+                                        channels_last=self.channels_last, **layer_kwargs)
+            self.num_conv += 1
+        self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp,
+                                    channels_last=self.channels_last, **layer_kwargs)
+        self.num_conv += 1
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, channels_last=self.channels_last)
+        self.num_torgb += 1
+
+    def _features(self, x, ws, force_fp32, fused_modconv, layer_kwargs):
+        misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
+        w_iter = iter(ws.unbind(dim=1))
+        dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
+        memory_format = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
+        if fused_modconv is None:
+            fused_modconv = (not self.training) and (dtype == torch.float32 or int(ws.shape[0]) == 1)
+        if self.in_channels == 0:
+            x = self.const.to(dtype=dtype, memory_format=memory_format)
+            x = x.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+        else:
+            misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
+            x = x.to(dtype=dtype, memory_format=memory_format)
+            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+        return x, next(w_iter), fused_modconv
+
+    def _accumulate(self, img, y):
+        """Skip connection: upsample the running image with the FIR and add the new contribution."""
+        if img is not None and img.shape[-1] * 2 == y.shape[-1]:
+            img = upfirdn2d.upsample2d(img, self.resample_filter)
+        y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+        return img.add_(y) if img is not None else y
+
+    def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, **layer_kwargs):
+        x, w_rgb, fused_modconv = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
+        img = self._accumulate(img, self.torgb(x, w_rgb, fused_modconv=fused_modconv))
+        return x, img
+
+
+@persistence.persistent_class
+class SegSynthesisBlock(SynthesisBlock):
+    """Dual-path block of the tri-plane backbone: one feature stream, two skip-accumulated outputs -- the texture
+    tri-plane `img` and the shape/semantic tri-plane `seg` (the dual ToRGB/ToSEG path of
+    inversion/networks.py:1093-1134).  Call contract from extract_shapes.py:127-129:
+        x, img, seg = block(x, img, ws, condition_img=seg)
+    Both heads share one style vector (`w_shared`, :1093) and are evaluated as ONE modulated 1x1 convolution whose
+    output channels are [img_channels | seg_channels], so the child list stays (conv0, conv1, torgb)."""
+
+    def __init__(self, in_channels, out_channels, w_dim, resolution, img_channels, seg_channels, is_last, **kwargs):
+        super().__init__(in_channels, out_channels, w_dim, resolution, img_channels + seg_channels, is_last, **kwargs)
+        self.img_channels, self.seg_channels = img_channels, seg_channels
+
+    def forward(self, x, img, ws, condition_img=None, force_fp32=False, fused_modconv=None, **layer_kwargs):
+        x, w_shared, fused_modconv = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
+        y = self.torgb(x, w_shared, fused_modconv=fused_modconv)
+        img = self._accumulate(img, y[:, :self.img_channels])
+        seg = self._accumulate(condition_img, y[:, self.img_channels:])
+        return x, img, seg

@@ -180,7 +180,7 @@ def filter2d(x, f, padding=0, flip_filter=False, gain=1):
 def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=math.sqrt(2), slope=0.2,
                    clamp=None, flip_filter=False, return_signs=False):
     """filtered_lrelu.py:121-153.  With return_signs also returns the packed 2-bit sign tensor the
-    plugin writes (filtered_lrelu.cpp:82-96): bit0 = value was negative, bit1 = value was clamped,
+    plugin writes (filtered_lrelu.cpp:82-96): code 1 = value was negative, code 2 = value was clamped (clamp wins),
     4 elements per byte in x order, width padded to a multiple of 16 elements."""
     px0, px1, py0, py1 = _pad4(padding)
     t = bias_act(x, b)
@@ -193,7 +193,8 @@ def filtered_lrelu(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=ma
     neg = (pre < 0)
     act = torch.where(neg, pre * slope, pre)
     clamped = (act.abs() > clamp) if clamp is not None else torch.zeros_like(neg)
-    code = neg.to(torch.uint8) | (clamped.to(torch.uint8) << 1)
+    # filtered_lrelu.cu:1135-1145: s = 1 for a negative value, overwritten by s = 2 when the value clamps
+    code = torch.where(clamped, torch.full_like(neg, 2, dtype=torch.uint8), neg.to(torch.uint8))
     n, c, sh, sw = code.shape
     swp = (sw + 15) // 16 * 16
     code = F.pad(code, [0, swp - sw])

@@ -161,7 +161,7 @@ def g_chain():
     n, S, res = 2, 12, (8, 8)
     tex = torch.randn(n, 96, 16, 16, generator=g)
     seg = torch.randn(n, 96, 16, 16, generator=g)
-    dec = orr.Decoder.random(hidden=16, seed=4, three_head=True)
+    dec = orr.Decoder.random(hidden=64, seed=4, three_head=True)      # the fused kernel's three-head shape
     cam = torch.from_numpy(ocam.look_at_pose(np.array([[1.3], [1.8]], np.float32), np.array([[1.5], [1.65]], np.float32),
                                              [0, 0, 0.2], radius=2.7, batch_size=2))
     box_scale = 2.0
@@ -181,6 +181,14 @@ def g_chain():
     save('chain', planes_tex=tex, planes_seg=seg, w1=dec.w1, b1=dec.b1, w2=dec.w2, b2=dec.b2, camera=cam, u=u,
          box_scale=box_scale, num_steps=S, resolution=np.array(res), rgb=rgb, depth=dep, weights=w,
          raw=raw, points_world=pw)
+    # same inputs through a dense 64 -> 64 -> 52 decoder (the fused kernel's single-head shape)
+    dd = orr.Decoder.random(hidden=64, seed=6, three_head=False)
+    rawd = dd(ft, fs).reshape(n, res[0] * res[1], S, 52)
+    rgbd, depd, wd = ref_vr.fancy_integration(rawd, d, zj, DEV, noise_std=0, clamp_mode='relu', last_back=True)
+    rod, dod, wod = orr.render_frames(tex, seg, dd, cam, fov=18.0, num_steps=S, ray_start=2.25, ray_end=3.3,
+                                      resolution=res, box_scale=box_scale, jitter_u=u, clamp_mode='relu', last_back=True)
+    close(rgbd, rod, tol=1e-5, what='chain_dense.rgb'); close(depd, dod, tol=1e-5, what='chain_dense.depth'); close(wd, wod, tol=1e-5, what='chain_dense.w')
+    save('chain_dense', w1=dd.w1, b1=dd.b1, w2=dd.w2, b2=dd.b2, rgb=rgbd, depth=depd, weights=wd)
     # sigma-only voxel query on the same planes (sample_voxel contract, extract_shapes.py:146)
     pts = torch.rand(n, 50, 3, generator=g) - 0.5
     sv = dec(ref_triplane(pts * box_scale, tex), ref_triplane(pts * box_scale, seg)).reshape(n, 50, 52)

@@ -1,0 +1,255 @@
+"""GPU parity: the fused renderer kernels and the stand-alone stages vs the CPU oracle and the recorded reference
+outputs.  Tolerances (fp32 path, stated per tensor): positions / depths 2e-6..1e-5 absolute; gathered features 5e-6;
+decoded / composited features 3e-5 absolute on O(1) values (hidden softplus uses MUFU ex2/lg2, |err| < 4e-7 each,
+summed over <= 192 hidden units); weights 1e-5."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import T, assert_close, load_golden
+from oracle import camera as ocam, renderer as orr
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def three_head_from_dense(w1, b1, w2, b2, H=64):
+    """Slice the block-sparse dense decoder of the fixtures into the three heads the kernel takes."""
+    w1, b1, w2, b2 = [torch.as_tensor(t) for t in (w1, b1, w2, b2)]
+    return [(0, 0, w1[0:H, 0:32], b1[0:H], w2[0:32, 0:H], b2[0:32]),
+            (1, 32, w1[H:2 * H, 32:], b1[H:2 * H], w2[32:51, H:2 * H], b2[32:51]),
+            (1, 51, w1[2 * H:, 32:], b1[2 * H:], w2[51:52, 2 * H:], b2[51:52])]
+
+
+@pytest.mark.parametrize('layout', ['nchw', 'nhwc'])
+def test_raymarch_matches_recorded_reference_chain(layout):
+    from ide3d_b200 import render
+    g = load_golden('chain')
+    tex, seg = T(g['planes_tex'], DEV), T(g['planes_seg'], DEV)
+    if layout == 'nhwc':
+        tex, seg = tex.contiguous(memory_format=torch.channels_last), seg.contiguous(memory_format=torch.channels_last)
+    heads = three_head_from_dense(g['w1'], g['b1'], g['w2'], g['b2'])
+    res = tuple(int(v) for v in g['resolution'])
+    feat, depth, w = render.raymarch(tex, seg, heads, T(g['camera'], DEV), resolution=res, num_steps=int(g['num_steps']),
+                                     box_scale=float(g['box_scale']), jitter_u=T(g['u'], DEV), return_weights=True,
+                                     convert_layout=(layout == 'nhwc'))
+    assert_close(feat, g['rgb'], 3e-5, what='feat')
+    assert_close(depth, g['depth'], 1e-5, what='depth')
+    assert_close(w, g['weights'], 1e-5, what='weights')
+
+
+def test_raymarch_dense_decoder_relu_lastback():
+    from ide3d_b200 import render
+    g, d = load_golden('chain'), load_golden('chain_dense')
+    res = tuple(int(v) for v in g['resolution'])
+    feat, depth, w = render.raymarch(T(g['planes_tex'], DEV), T(g['planes_seg'], DEV),
+                                     render.dense_heads(*[T(d[k]) for k in ('w1', 'b1', 'w2', 'b2')]), T(g['camera'], DEV),
+                                     resolution=res, num_steps=int(g['num_steps']), box_scale=float(g['box_scale']),
+                                     jitter_u=T(g['u'], DEV), clamp_mode='relu', last_back=True, return_weights=True)
+    assert_close(feat, d['rgb'], 3e-5); assert_close(depth, d['depth'], 1e-5); assert_close(w, d['weights'], 1e-5)
+
+
+def _random_case(n, plane, seed, hidden=64, three_head=True):
+    g = torch.Generator().manual_seed(seed)
+    tex = torch.randn(n, 96, plane, plane, generator=g)
+    seg = torch.randn(n, 96, plane, plane, generator=g)
+    dec = orr.Decoder.random(hidden=hidden, seed=seed + 1, three_head=three_head)
+    yaw = math.pi / 2 + np.linspace(-0.5, 0.5, n).reshape(n, 1).astype(np.float32)
+    pitch = np.full((n, 1), math.pi / 2 - 0.1, np.float32)
+    cam = torch.from_numpy(ocam.look_at_pose(yaw, pitch, [0, 0, 0.2], radius=2.7, batch_size=n))
+    return tex, seg, dec, cam
+
+
+@pytest.mark.parametrize('S,res,opts', [
+    (48, (16, 16), dict()),                                              # config-1 shape, small image
+    (96, (12, 10), dict(white_back=True, max_depth=3.3)),                # 3 full chunks, non-square, odd tile edge
+    (33, (9, 7), dict(last_back=True, clamp_mode='relu')),               # ragged chunk
+    (1, (5, 5), dict()),                                                 # single sample (delta = 1e10 only)
+    (40, (8, 8), dict(fill_mode='weight')),
+])
+def test_raymarch_vs_oracle_random(S, res, opts):
+    from ide3d_b200 import render
+    tex, seg, dec, cam = _random_case(2, 32, seed=S)
+    u = torch.rand(2, res[0] * res[1], S, 1, generator=torch.Generator().manual_seed(5))
+    ro, do_, wo = orr.render_frames(tex, seg, dec, cam, num_steps=S, resolution=res, jitter_u=u, **opts)
+    heads = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
+    feat, depth, w = render.raymarch(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=res, num_steps=S,
+                                     jitter_u=u.to(DEV), return_weights=True, **opts)
+    assert_close(feat, ro, 3e-5, what='feat'); assert_close(depth, do_, 1e-5, what='depth'); assert_close(w, wo, 1e-5, what='w')
+
+
+def test_raymarch_hash_jitter_is_bit_compatible_with_oracle_hash():
+    from ide3d_b200 import render
+    tex, seg, dec, cam = _random_case(2, 24, seed=11, hidden=128, three_head=False)
+    S, res, seed = 20, (8, 8), 0x1234_5678_9ABC_DEF1
+    ro, do_, wo = orr.render_frames(tex, seg, dec, cam, num_steps=S, resolution=res, jitter_seed=seed)
+    feat, depth, w = render.raymarch(tex.to(DEV), seg.to(DEV), render.dense_heads(dec.w1, dec.b1, dec.w2, dec.b2),
+                                     cam.to(DEV), resolution=res, num_steps=S, jitter_seed=seed, return_weights=True)
+    assert_close(feat, ro, 3e-5); assert_close(depth, do_, 1e-5); assert_close(w, wo, 1e-5)
+
+
+def test_raymarch_noise_and_no_jitter():
+    from ide3d_b200 import render
+    tex, seg, dec, cam = _random_case(1, 16, seed=3)
+    S, res = 12, (6, 6)
+    noise = torch.randn(1, 36, S, 1, generator=torch.Generator().manual_seed(2))
+    ro, do_, wo = orr.render_frames(tex, seg, dec, cam, num_steps=S, resolution=res, noise=noise, noise_std=0.7)
+    feat, depth, w = render.raymarch(tex.to(DEV), seg.to(DEV), three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2),
+                                     cam.to(DEV), resolution=res, num_steps=S, noise=noise.to(DEV), noise_std=0.7,
+                                     return_weights=True)
+    assert_close(feat, ro, 3e-5); assert_close(depth, do_, 1e-5); assert_close(w, wo, 1e-5)
+
+
+def test_raymarch_full_size_properties():
+    """BASELINE config 2 shape (8 frames, 64^2 x 96, 256^2 planes): size-independent properties instead of the slow
+    CPU oracle -- weights are a sub-probability along each ray, last_back makes them sum to 1, fill_mode='weight'
+    returns exactly the weight sums, linearity of the composited features in the decoder's output bias."""
+    from ide3d_b200 import render
+    g = torch.Generator(device='cuda').manual_seed(0)
+    n = 8
+    tex = torch.randn(n, 256, 256, 96, device=DEV, generator=g).permute(0, 3, 1, 2)
+    seg = torch.randn(n, 256, 256, 96, device=DEV, generator=g).permute(0, 3, 1, 2)
+    dec = orr.Decoder.random(hidden=64, seed=1)
+    heads = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
+    yaw = math.pi / 2 + np.linspace(-0.5, 0.5, n).reshape(n, 1).astype(np.float32)
+    cam = torch.from_numpy(ocam.look_at_pose(yaw, np.full((n, 1), math.pi / 2, np.float32), [0, 0, 0.2], radius=2.7, batch_size=n)).to(DEV)
+    kw = dict(resolution=(64, 64), num_steps=96, jitter_seed=7, return_weights=True)
+    feat, depth, w = render.raymarch(tex, seg, heads, cam, **kw)
+    wsum = w.sum(2)
+    assert torch.isfinite(feat).all() and torch.isfinite(depth).all()
+    assert (w >= 0).all() and (wsum <= 1 + 1e-4).all()
+    assert (depth >= 2.25 * wsum - 1e-3).all() and (depth <= 3.3 * wsum + 1e-3).all()
+    _, _, w_lb = render.raymarch(tex, seg, heads, cam, last_back=True, **kw)
+    assert_close(w_lb.sum(2), torch.ones_like(wsum), 2e-5, what='last_back sums to one')
+    f_fill, _, _ = render.raymarch(tex, seg, heads, cam, fill_mode='weight', **kw)
+    assert_close(f_fill, wsum.expand(-1, -1, 51), 2e-5, what='fill_mode=weight')
+    # shifting the colour head's output bias by delta shifts the composited colour by delta * wsum
+    heads2 = [(heads[0][0], heads[0][1], heads[0][2], heads[0][3], heads[0][4], heads[0][5] + 0.5)] + heads[1:]
+    f2, _, _ = render.raymarch(tex, seg, heads2, cam, **kw)
+    assert_close(f2[..., :32] - feat[..., :32], 0.5 * wsum.expand(-1, -1, 32), 5e-5, what='bias linearity')
+    assert_close(f2[..., 32:], feat[..., 32:], 0.0, what='other heads untouched')
+    # a spot-check of 3 rays of frame 5 against the oracle on the same inputs
+    sub = slice(5, 6)
+    ro, do_, _ = orr.render_frames(tex[sub].cpu().contiguous(), seg[sub].cpu().contiguous(), dec, cam[sub].cpu(),
+                                   num_steps=96, resolution=(64, 64), jitter_u=None)
+    f_nj, d_nj, _ = render.raymarch(tex[sub], seg[sub], heads, cam[sub], resolution=(64, 64), num_steps=96)
+    assert_close(f_nj, ro, 5e-5, what='full-size frame vs oracle'); assert_close(d_nj, do_, 2e-5)
+
+
+def test_unsupported_decoder_shape_is_reported():
+    from ide3d_b200 import render
+    tex = torch.randn(1, 96, 8, 8, device=DEV)
+    bad = [(2, 0, torch.randn(48, 64), torch.zeros(48), torch.randn(52, 48), torch.zeros(52))]
+    with pytest.raises(RuntimeError, match='no fused kernel'):
+        render.raymarch(tex, tex, bad, torch.eye(4, device=DEV)[None], resolution=(4, 4), num_steps=4)
+    with pytest.raises(ValueError):
+        render.raymarch(tex, tex, bad, torch.eye(4, device=DEV)[None], clamp_mode=None)
+
+
+# ------------------------------------------------------------------------------------------ point queries
+def test_sample_voxel_golden_and_edges():
+    from ide3d_b200 import render
+    g, v = load_golden('chain'), load_golden('voxel')
+    heads = three_head_from_dense(g['w1'], g['b1'], g['w2'], g['b2'])
+    tex, seg = T(g['planes_tex'], DEV), T(g['planes_seg'], DEV)
+    out = render.sample_voxel(tex, seg, heads, T(v['points'], DEV), box_scale=float(g['box_scale']))
+    assert_close(out, v['out'], 3e-5)
+    sg = render.sample_voxel(tex, seg, heads, T(v['points'], DEV), box_scale=float(g['box_scale']), sigma_only=True)
+    assert_close(sg, v['out'][..., -1:], 3e-5)
+    # ragged count (not a multiple of 32), far-outside points (all taps masked) and an empty request
+    pts = torch.cat([T(v['points'])[:, :37], torch.full((2, 3, 3), 9.0)], 1)
+    dec = orr.Decoder(g['w1'], g['b1'], g['w2'], g['b2'])
+    ref = orr.sample_voxel(T(g['planes_tex']), T(g['planes_seg']), dec, pts, float(g['box_scale']))
+    assert_close(render.sample_voxel(tex, seg, heads, pts.to(DEV), box_scale=float(g['box_scale'])), ref, 3e-5)
+    assert render.sample_voxel(tex, seg, heads, torch.zeros(2, 0, 3, device=DEV)).shape == (2, 0, 52)
+
+
+def test_sigma_grid_matches_create_samples_path():
+    from ide3d_b200 import render
+    tex, seg, dec, _ = _random_case(1, 32, seed=21)
+    heads = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
+    N = 24
+    samples, _, _ = orr.create_samples(N, [0, 0, 0], 1.0)
+    ref = orr.sample_voxel(tex, seg, dec, 0.9 * samples, 2.0)[..., -1]
+    full = render.sigma_grid(tex.to(DEV), seg.to(DEV), heads, grid_n=N, cube_length=1.0)
+    assert_close(full, ref, 3e-5)
+    # slab interface = what a rank computes in the z-slab shard; concatenation must equal the whole grid (bit-exact)
+    cut = 5000
+    a = render.sigma_grid(tex.to(DEV), seg.to(DEV), heads, grid_n=N, cube_length=1.0, first=0, count=cut)
+    b = render.sigma_grid(tex.to(DEV), seg.to(DEV), heads, grid_n=N, cube_length=1.0, first=cut)
+    assert torch.equal(torch.cat([a, b], 1), full)
+    # and the explicit-points kernel agrees with the in-kernel point generator
+    exp = render.sample_voxel(tex.to(DEV), seg.to(DEV), heads, (0.9 * samples).to(DEV), sigma_only=True)[..., 0]
+    assert_close(full, exp, 1e-6)
+
+
+# ------------------------------------------------------------------------------------------ stand-alone stages
+def test_free_functions_match_recorded_reference():
+    from ide3d_b200.training import volumetric_rendering as vr
+    for tag in 'ab':
+        g = load_golden('rays_' + tag)
+        p, z, d = vr.get_initial_rays_trig(int(g['n']), int(g['num_steps']), DEV, float(g['fov']),
+                                           tuple(int(v) for v in g['resolution']), float(g['ray_start']), float(g['ray_end']))
+        assert_close(p, g['points'], 2e-6); assert_close(z, g['z_vals'], 2e-6); assert_close(d, g['rays_d_cam'], 2e-6)
+    g = load_golden('transform')
+    torch.manual_seed(123)
+    u = torch.rand(g['z_vals'].shape, device=DEV)          # the draw transform_sampled_points makes first
+    torch.manual_seed(123)
+    pw, zj, dw, ow, _, _ = vr.transform_sampled_points(T(g['points'], DEV), T(g['z_vals'], DEV), T(g['rays_d_cam'], DEV),
+                                                       DEV, camera=T(g['camera'], DEV))
+    pj, zo = orr.perturb(T(g['points']), T(g['z_vals']), T(g['rays_d_cam']), u.cpu())
+    pwo, dwo, owo = orr.to_world(pj, T(g['rays_d_cam']), T(g['camera']))
+    assert_close(zj, zo, 2e-6); assert_close(pw, pwo, 3e-6); assert_close(dw, dwo, 2e-6); assert_close(ow, owo, 2e-6)
+
+
+def test_sample_from_triplane_golden():
+    from ide3d_b200.dnnlib.util import sample_from_triplane
+    g = load_golden('triplane')
+    for fmt in (torch.contiguous_format, torch.channels_last):
+        out = sample_from_triplane(T(g['coords'], DEV), T(g['grid'], DEV).contiguous(memory_format=fmt))
+        assert_close(out, g['feat'], 5e-6)
+
+
+@pytest.mark.parametrize('case,kw', [
+    ('softplus', dict(clamp_mode='softplus')), ('relu', dict(clamp_mode='relu')),
+    ('lastback', dict(clamp_mode='softplus', last_back=True)),
+    ('white', dict(clamp_mode='softplus', white_back=True, max_depth=3.5)),
+    ('fillw', dict(clamp_mode='relu', fill_mode='weight'))])
+def test_fancy_integration_golden(case, kw):
+    from ide3d_b200.training import volumetric_rendering as vr
+    g = load_golden('integration')
+    rgb, dep, w = vr.fancy_integration(T(g['rgb_sigma'], DEV), T(g['rays_d_cam'], DEV), T(g['z_vals'], DEV), DEV,
+                                       noise_std=0, **kw)
+    assert_close(rgb, g[case + '_rgb'], 1e-5); assert_close(dep, g[case + '_depth'], 1e-5); assert_close(w, g[case + '_weights'], 5e-6)
+
+
+def test_fancy_integration_needs_clamp_mode():
+    from ide3d_b200.training import volumetric_rendering as vr
+    g = load_golden('integration')
+    with pytest.raises(ValueError):
+        vr.fancy_integration(T(g['rgb_sigma'], DEV), T(g['rays_d_cam'], DEV), T(g['z_vals'], DEV), DEV, noise_std=0)
+
+
+def test_sample_pdf_golden():
+    from ide3d_b200.training import volumetric_rendering as vr
+    g = load_golden('sample_pdf')
+    assert_close(vr.sample_pdf(T(g['bins'], DEV), T(g['weights'], DEV), 8, det=True), g['det'], 5e-6)
+    torch.manual_seed(9)
+    u = torch.rand(g['bins'].shape[0], 8, device=DEV)
+    torch.manual_seed(9)
+    out = vr.sample_pdf(T(g['bins'], DEV), T(g['weights'], DEV), 8, det=False)
+    assert_close(out, orr.sample_pdf(T(g['bins']), T(g['weights']), 8, det=False, u=u.cpu()), 5e-6)
+
+
+def test_camera_helpers_golden():
+    from ide3d_b200.training import volumetric_rendering as vr
+    g = load_golden('camera')
+    for i, (h, v) in enumerate(zip(g['h'], g['v'])):
+        o, _, _ = vr.sample_camera_positions(DEV, n=1, r=2.7, horizontal_mean=float(h), vertical_mean=float(v), mode=None)
+        assert_close(o, g[f'origin{i}'], 2e-6)
+        assert_close(vr.create_cam2world_matrix(-o, o, device=DEV), g[f'c2w{i}'], 2e-6)
+        la = vr.LookAtPoseSampler.sample(float(h), float(v), torch.tensor([0, 0, 0.2], device=DEV), radius=2.7, device=DEV)
+        assert_close(la, g[f'lookat{i}'], 2e-6)
