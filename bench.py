@@ -1,0 +1,307 @@
+#!/usr/bin/env python
+"""bench.py -- rendered frames/sec at 64^2 neural x 96 samples -> 512^2 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...)
+
+A "step" is one pass of the hot path over one batch: G.synthesis(ws, c) for 8 latents of the random-init
+ide3d-ffhq-64-512 generator (tri-plane backbone -> fused ray-march at 64^2 x 96 -> super-resolution to 512^2), yaw
+sweep -- BASELINE.json configs[1].  Weak scaling: every rank renders its own 8-frame batch.
+
+value : whole-job frames/s with ws / cameras already resident in HBM (CUDA events, max over ranks, L2 flushed
+        between timed iterations).
+e2e   : the same metric through the public call a user makes (render_frames_sharded: host ws / cameras -> H2D from
+        pinned memory -> synthesis -> uint8 frames -> all_gather over NCCL when N > 1 -> D2H), copies inside the
+        timed region.
+roofline : the fused ray-march kernel (dominant kernel of the renderer), timed live with CUDA events on its stream
+        inside the synthesis steps; algorithmic bytes = 51.20 MB per frame (both tri-planes once + outputs).
+cpu_baseline : the oracle port (stock torch-CPU ops chained like the reference's free functions) on the host cores,
+        bounded sample = 1 frame of the same workload.
+--impl reference : that CPU path as the timed arm (rank 0 only).
+"""
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+BATCH = 8
+NUM_STEPS = 96
+RENDER = 64
+PLANE = 256
+FRAME_ALGO_BYTES = 2 * 96 * PLANE * PLANE * 4 + RENDER * RENDER * (32 + 19 + 1 + 1) * 4   # 51.20 MB
+METRIC = 'rendered frames/sec at 64^2 neural x 96 samples -> 512^2'
+
+
+def make_labels(n):
+    """Host labels: cam2world from the product's own pose helpers (training/volumetric_rendering.py:147-213)."""
+    from ide3d_b200.training.volumetric_rendering import create_cam2world_matrix, sample_camera_positions
+    yaws = math.pi / 2 + torch.linspace(-0.5, 0.5, n)
+    intr = torch.tensor([4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1], dtype=torch.float32)
+    cs = []
+    for y in yaws:
+        o, _, _ = sample_camera_positions('cpu', n=1, r=2.7, horizontal_mean=float(y), vertical_mean=math.pi / 2, mode=None)
+        m = create_cam2world_matrix(-o, o, device='cpu')
+        cs.append(torch.cat([m.reshape(1, 16), intr.reshape(1, 9)], 1))
+    return torch.cat(cs)
+
+
+def make_latents(n, z_dim, offset=0):
+    return torch.from_numpy(np.stack([np.random.RandomState(offset + i).randn(z_dim) for i in range(n)])).float()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.index}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([v.strip() for v in line.split(',')])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.25)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), r[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        if not sm:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable'], 'samples': 0}
+        return {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+def cpu_reference_fps(G_cpu, ws1, c1, reps):
+    """Oracle port on the host cores: full synthesis of ONE frame of the same workload, all threads."""
+    from oracle.backend import cpu_reference_ops
+    times = []
+    with torch.no_grad(), cpu_reference_ops():
+        G_cpu.synthesis(ws1, c=c1, render_params=dict(num_steps=NUM_STEPS), noise_mode='const', perturb='hash', seed=1)   # warm-up
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            G_cpu.synthesis(ws1, c=c1, render_params=dict(num_steps=NUM_STEPS), noise_mode='const', perturb='hash', seed=1)
+            times.append(time.perf_counter() - t0)
+    return 1.0 / float(np.mean(times)), float(np.mean(times))
+
+
+def build_generator(device):
+    from ide3d_b200.compat import random_init_generator
+    return random_init_generator(device=device, seed=0)
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path is the timed arm.  Rank 0 only; other ranks exit 0 without work."""
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    G = build_generator('cpu')
+    z = make_latents(1, G.z_dim)
+    c = make_labels(BATCH)[BATCH // 2:BATCH // 2 + 1]
+    from oracle.backend import cpu_reference_ops
+    with torch.no_grad(), cpu_reference_ops():
+        ws = G.mapping(z, c)
+    kw = dict(render_params=dict(num_steps=NUM_STEPS), noise_mode='const', perturb='hash', seed=1)
+    with torch.no_grad(), cpu_reference_ops():
+        G.synthesis(ws, c=c, **kw)                      # one untimed warm-up (each step is ~10 s of CPU work)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            G.synthesis(ws, c=c, **kw)
+        dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cores = torch.get_num_threads()
+    sample = '1 frame per step (of the 8-frame batch): full synthesis backbone -> 64^2x96 render -> 512^2 SR, torch-CPU ops'
+    line = {'impl': 'reference', 'metric': METRIC, 'value': fps, 'unit': 'frames/s', 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: 64^2 x 96 -> 512^2, random-init ide3d-ffhq-64-512, yaw sweep', 'frames_per_step': 1,
+                       'arm': 'oracle port of the reference PyTorch path on host cores'},
+            'cpu_baseline': {'value': fps, 'unit': 'frames/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': fps, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--cpu-reps', type=int, default=2, help='timed repetitions of the 1-frame CPU baseline')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+
+    if args.impl == 'reference':
+        run_reference(args, int(os.environ.get('RANK', '0')))
+        return
+
+    from ide3d_b200 import _lib, dist as idist, render
+    rank, world, device = idist.init_from_env()
+    assert device.type == 'cuda', 'bench.py needs a CUDA device (the product has no CPU path)'
+    assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'
+    import torch.distributed as tdist
+    torch.backends.cudnn.benchmark = True
+
+    G = build_generator(device)
+    z_host = make_latents(BATCH, G.z_dim, offset=rank * BATCH)
+    c_host = make_labels(BATCH)
+    with torch.no_grad():
+        ws = G.mapping(z_host.to(device), c_host.to(device))
+    c = c_host.to(device)
+    kw = dict(render_params=dict(num_steps=NUM_STEPS), noise_mode='const')
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)      # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return G.synthesis(ws, c=c, **kw)
+
+    # pinned host buffers for the e2e leg
+    ws_pin = ws.cpu().pin_memory()
+    c_pin = c_host.pin_memory()
+
+    def step_e2e():
+        frames = idist.render_frames_sharded(G, ws_pin, c_pin, 0, 1, batch=BATCH, **kw)     # this rank's 8 frames
+        if world > 1:
+            allf = torch.empty((world,) + tuple(frames.shape), dtype=frames.dtype, device=device)
+            tdist.all_gather_into_tensor(allf, frames)
+            frames = allf if rank == 0 else frames
+        return frames.cpu() if rank == 0 else frames
+
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            step()
+        step_e2e()
+        barrier()
+
+        # ---------------- value: device-resident inputs, per-iteration events, L2 flushed between iterations
+        render.kernel_events = []
+        launches0 = _lib.launch_count()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        with ClockSampler(device.index or 0) as clocks:
+            barrier()
+            for a, b in ev:
+                flush.zero_()
+                a.record()
+                step()
+                b.record()
+            barrier()
+        launches = _lib.launch_count() - launches0
+        dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+        kern = render.kernel_events
+        render.kernel_events = None
+        kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in kern]))
+
+        # ---------------- e2e: host inputs, copies inside the timed region
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in ev2:
+            a.record()
+            step_e2e()
+            b.record()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+
+        # ---------------- renderer only (planes resident, channels-last): the kernel's own throughput per frame
+        voxel_ws, _ = G.synthesis.split_ws(ws)
+        img_v, seg_v = G.synthesis.backbone(voxel_ws, noise_mode='const')
+        cam = c[:, :16].reshape(-1, 4, 4)
+        ev3 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b in ev3:
+            flush.zero_()
+            a.record()
+            G.synthesis.renderer(img_v, seg_v, cam, img_size=RENDER, num_steps=NUM_STEPS)   # NCHW planes in: 2 layout passes + ray-march
+            b.record()
+        torch.cuda.synchronize()
+        renderer_ms = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
+
+    t = torch.tensor([dev_ms, e2e_wall * 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        tdist.all_reduce(t, op=tdist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        frames_total = BATCH * args.steps * world
+        value = frames_total / (dev_ms * 1e-3)
+        e2e_value = frames_total / (e2e_ms * 1e-3)
+        achieved = BATCH * FRAME_ALGO_BYTES / (kern_ms * 1e-3) / 1e9
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'frames/s', 'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+            'ms_per_step': dev_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'configs[1]: batch=8 latents, 64^2 neural render x 96 samples -> 512^2 SR, yaw sweep, '
+                                   'random-init ide3d-ffhq-64-512 (TriPlaneGenerator seed 0)',
+                       'frames_per_step_per_gpu': BATCH, 'plane': [96, PLANE, PLANE], 'l2': 'flushed (256 MB write) between timed iterations',
+                       'timing': 'CUDA events per iteration on the launching stream, max over ranks', 'parallelism': f'frames sharded x{world}, no data-path collective'},
+            'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(ws_pin.numel() * 4 + c_pin.numel() * 4),
+                    'd2h_bytes_per_step': int(BATCH * world * 3 * 512 * 512), 'call': 'ide3d_b200.dist.render_frames_sharded (pinned host ws/c -> uint8 frames on host)'},
+            'gpu_launches': int(launches),
+            'roofline': {'kernel': 'raymarch_kernel (fused gather + MLP + compositing)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src, 'kernel_ms': kern_ms,
+                         'algorithmic_bytes_per_launch': BATCH * FRAME_ALGO_BYTES,
+                         'kernel_only_fps': BATCH / (kern_ms * 1e-3), 'renderer_fps_incl_layout_pass': BATCH / (renderer_ms * 1e-3),
+                         'note': 'gather is served by L1/L2 (both tri-planes fit in L2): HBM fraction is low by construction; see profiles/'},
+            'clocks': clocks.summary(),
+        }
+        if not args.no_cpu_baseline and world == 1:
+            torch.set_num_threads(os.cpu_count() or 1)
+            Gc = build_generator('cpu')
+            fps, sec = cpu_reference_fps(Gc, ws[:1].cpu(), c_host[:1], args.cpu_reps)
+            line['cpu_baseline'] = {'value': fps, 'unit': 'frames/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                                    'sample': f'1 frame of the batch (full synthesis, {sec:.1f} s each, {args.cpu_reps} reps + 1 warm-up), oracle port on torch-CPU ops'}
+        print(json.dumps(line))
+    if world > 1:
+        tdist.barrier()
+        tdist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

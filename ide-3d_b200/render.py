@@ -13,6 +13,10 @@ from . import _lib as L
 
 N_FEAT, N_SEG, N_OUT = 32, 19, 52
 
+# When set to a list, every fused ray-march launch appends (start_event, end_event, frames) recorded on the launching
+# stream -- how bench.py measures the kernel's own duration live inside the full synthesis step.
+kernel_events = None
+
 
 class PackedDecoder:
     """fp32 device copies of the head parameters plus the C struct that points at them (kept alive together)."""
@@ -98,7 +102,13 @@ def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), nu
     p.max_depth, p.fill_weight = float(max_depth or 0.0), int(fill_mode == 'weight')
     p.out_feat, p.out_depth, p.out_weights = L.ptr(feat), L.ptr(depth), L.ptr(weights)
     with torch.cuda.device(dev):
+        if kernel_events is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
         L.check(L.get_lib().ide3d_raymarch_fwd(C.byref(p), L.stream_ptr(dev)))
+        if kernel_events is not None:
+            e1.record()
+            kernel_events.append((e0, e1, n))
     return feat, depth, weights
 
 

@@ -28,7 +28,8 @@ def test_bias_act_golden_all_activations():
     assert ba.bias_act(x, None, act='linear') is x                      # identity short-cut
 
 
-@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 1e-5, 0), (torch.float16, 2e-3, 1e-2), (torch.float64, 1e-12, 0)])
+# fp64: alpha/gain/clamp travel as float32 in the parameter block (bias_act.h:22-24), hence 1e-7 not 1e-15
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 1e-5, 0), (torch.float16, 2e-3, 1e-2), (torch.float64, 2e-7, 2e-7)])
 @pytest.mark.parametrize('shape,dim,cl', [((3, 7, 5, 9), 1, False), ((2, 8, 6, 6), 1, True), ((5, 33), 1, False), ((1031,), 0, False)])
 def test_bias_act_layouts_dtypes(dtype, atol, rtol, shape, dim, cl):
     from ide3d_b200.torch_utils.ops import bias_act as ba
@@ -98,7 +99,7 @@ def test_upfirdn2d_golden():
     assert_close(up.filter2d(x, f), g['filter2d'], 1e-5)
 
 
-@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2), (torch.float64, 1e-12, 0)])
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2), (torch.float64, 2e-7, 2e-7)])
 @pytest.mark.parametrize('hw', [(64, 64), (70, 37), (129, 200)])
 def test_upfirdn2d_stylegan_shapes(dtype, atol, rtol, hw):
     """The three hot StyleGAN2 specialisations + separable 12-tap passes, on tile-unfriendly sizes, contiguous and
