@@ -65,8 +65,9 @@ def all_gather_slabs(local, total, world):
     per = base + (1 if rem else 0)
     pad = torch.zeros(tuple(local.shape[:-1]) + (per,), dtype=local.dtype, device=local.device)
     pad[..., :local.shape[-1]] = local
-    out = torch.empty((world,) + tuple(pad.shape), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, pad.contiguous())
+    out = torch.empty((world * pad.shape[0],) + tuple(pad.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad.contiguous())          # concatenation along dim 0 (gloo and nccl agree on this form)
+    out = out.reshape((world,) + tuple(pad.shape))
     parts = [out[r][..., :base + (1 if r < rem else 0)] for r in range(world)]
     return torch.cat(parts, dim=-1)
 

@@ -1,0 +1,131 @@
+"""CPU: host-side logic of the generator / plugin shims with the CUDA entry points swapped for the oracle
+(oracle.backend.cpu_reference_ops) -- API contract reconstructed from the reference's call sites."""
+
+import math
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle.backend import cpu_reference_ops
+
+LABEL = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 2.7, 0, 0, 0, 1, 4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1]   # gen_images.py:87
+
+
+@pytest.fixture(scope='module')
+def G():
+    from ide3d_b200.training.triplane import TriPlaneGenerator
+    torch.manual_seed(0)
+    return TriPlaneGenerator(z_dim=32, w_dim=32, img_resolution=64, plane_resolution=32, render_size=16, channel_base=1024,
+                             channel_max=32, sr_channels=(16, 8), mapping_kwargs=dict(num_layers=2)).eval().requires_grad_(False)
+
+
+def test_full_size_generator_has_the_reference_layer_structure():
+    """7 backbone blocks (3 children each: conv0?, conv1, torgb), 3 renderer heads, 2 SR blocks, 18 ws
+    (ide3d-nada/ZSSGAN/model/ZSSGAN_IDE3D.py:425-437; apps/train_hybrid_encoder.py:40-43)."""
+    from ide3d_b200.training.triplane import TriPlaneGenerator
+    g = TriPlaneGenerator()
+    s = g.synthesis
+    assert g.num_ws == s.num_ws == g.mapping.num_ws == g.backbone.num_ws == 18
+    assert (g.z_dim, g.c_dim, g.w_dim, g.img_resolution, g.img_channels) == (512, 25, 512, 512, 3)
+    assert s.voxel_block_resolutions == [4, 8, 16, 32, 64, 128, 256] and s.block_resolutions == [256, 512]
+    assert s.render_size == g.neural_rendering_resolution == 64
+    layers = [l for child in s.children() for l in child.children()]
+    names = [type(l).__name__ for l in layers]
+    assert len(layers) == 29 and names[:2] == ['SynthesisLayer', 'ToRGBLayer']
+    assert names[20:23] == ['DecoderHead'] * 3                                   # the "nerf" layers, idx 20-22
+    conv_inds = [0, 2, 3, 5, 6, 8, 9, 11, 12, 14, 15, 17, 18, 23, 24, 26, 27]
+    rgb_inds = [1, 4, 7, 10, 13, 16, 19, 25, 28]
+    assert all(names[i] == 'SynthesisLayer' for i in conv_inds) and all(names[i] == 'ToRGBLayer' for i in rgb_inds)
+    assert g.rendering_kwargs['ray_start'] == 2.25 and g.rendering_kwargs['ray_end'] == 3.3 and g.rendering_kwargs['fov'] == 18.0
+    assert set(g.init_kwargs) == set() and g.init_args == ()
+    assert any('noise_const' in n for n, _ in s.named_buffers())
+
+
+def test_synthesis_contract(G):
+    z = torch.randn(2, G.z_dim)
+    c = torch.tensor(LABEL).repeat(2, 1)
+    with cpu_reference_ops():
+        ws = G.mapping(z, c, truncation_psi=0.7, truncation_cutoff=4)
+        assert ws.shape == (2, G.num_ws, G.w_dim)
+        img = G.synthesis(ws, c=c, noise_mode='const', render_params=dict(num_steps=8, h_mean=1.2, fov=18))
+        img2, seg = G.synthesis(ws, c=c, noise_mode='const', return_seg=True, render_params=dict(num_steps=8))
+        img3, raw = G.synthesis(ws, c, return_raw=True, force_fp32=True, num_steps=8)
+        d = G.synthesis(ws, c=c, return_dict=True, num_steps=8)
+        img_nolabel = G.synthesis(ws, render_params=dict(num_steps=8, h_mean=math.pi / 2, v_mean=math.pi / 2), perturb=None)
+        img_label = G.synthesis(ws, c=c, num_steps=8, perturb=None)
+    assert img.shape == img2.shape == img3.shape == (2, 3, 64, 64) and seg.shape == (2, 19, 64, 64) and raw.shape == (2, 3, 16, 16)
+    assert set(d) >= {'image', 'image_raw', 'image_depth'} and d['image_depth'].shape == (2, 1, 16, 16)
+    assert torch.isfinite(img).all() and torch.isfinite(seg).all()
+    # the frontal label IS the pose sample_camera_positions(pi/2, pi/2, r=2.7) builds: both routes agree
+    assert torch.allclose(img_nolabel, img_label, atol=1e-5)
+
+
+def test_block_walk_of_extract_shapes(G):
+    """The exact loop of extract_shapes.py:113-147 runs against the generator."""
+    from ide3d_b200.torch_utils import misc
+    z = torch.randn(1, G.z_dim)
+    c = torch.tensor(LABEL)[None]
+    with cpu_reference_ops():
+        ws = G.mapping(z, c, truncation_psi=0.5)
+        misc.assert_shape(ws, [None, G.synthesis.num_ws, G.synthesis.w_dim])
+        voxel_block_ws, block_ws, w_idx = [], [], 0
+        for res in G.synthesis.voxel_block_resolutions:
+            block = getattr(G.synthesis, f'vb{res}')
+            voxel_block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
+            w_idx += block.num_conv
+        for res in G.synthesis.block_resolutions:
+            block = getattr(G.synthesis, f'b{res}')
+            block_ws.append(ws.narrow(1, w_idx, block.num_conv + block.num_torgb))
+            w_idx += block.num_conv
+        assert w_idx + 1 == G.synthesis.num_ws
+        x_v = img_v = seg_v = None
+        for res, cur_ws in zip(G.synthesis.voxel_block_resolutions, voxel_block_ws):
+            x_v, img_v, seg_v = getattr(G.synthesis, f'vb{res}')(x_v, img_v, cur_ws, condition_img=seg_v)
+        assert img_v.shape == seg_v.shape == (1, 96, 32, 32)
+        samples = torch.rand(1, 250, 3) - 0.5
+        out = G.synthesis.renderer.sample_voxel(img_v, seg_v, samples[:, 0:100]).reshape(samples.size(0), -1, 52)
+        assert out.shape == (1, 100, 52)
+        a, b = G.synthesis.split_ws(ws)
+        assert all(torch.equal(x, y) for x, y in zip(a + b, voxel_block_ws + block_ws))
+
+
+def test_compat_aliases_and_persistence(G):
+    import ide3d_b200.compat as compat
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split('.')[0] in ('training', 'torch_utils')}
+    try:
+        names = compat.install()
+        from training.triplane import TriPlaneGenerator as A                       # noqa: the reference's import lines
+        from training.volumetric_rendering import LookAtPoseSampler, create_cam2world_matrix, sample_camera_positions  # noqa
+        from torch_utils.ops import bias_act, filtered_lrelu, upfirdn2d             # noqa
+        from torch_utils import custom_ops, misc, persistence                      # noqa
+        assert 'training.triplane' in names and A is type(G).__mro__[0] or issubclass(type(G), A.__mro__[1])
+    finally:
+        for k in list(sys.modules):
+            if k.split('.')[0] in ('training', 'torch_utils'):
+                del sys.modules[k]
+        sys.modules.update({k: v for k, v in saved.items() if v is not None})
+    # viz/renderer.py:199 style re-instantiation
+    G2 = type(G)(*G.init_args, **G.init_kwargs)
+    assert G2.num_ws == G.num_ws and sum(p.numel() for p in G2.parameters()) == sum(p.numel() for p in G.parameters())
+
+
+def test_pose_helpers_cpu():
+    from ide3d_b200.training.volumetric_rendering import LookAtPoseSampler, create_cam2world_matrix, sample_camera_positions
+    o, phi, theta = sample_camera_positions('cpu', n=3, r=2.7, horizontal_mean=math.pi / 2, vertical_mean=math.pi / 2, mode=None)
+    m = create_cam2world_matrix(-o, o, device='cpu')
+    assert torch.allclose(m[0].reshape(-1), torch.tensor(LABEL[:16]), atol=1e-6)
+    la = LookAtPoseSampler.sample(math.pi / 2, math.pi / 2, torch.tensor([0, 0, 0.]), radius=2.7)
+    assert torch.allclose(la, m[:1], atol=1e-6)
+    torch.manual_seed(1)
+    for mode in ('uniform', 'normal', 'hybrid', 'truncated_gaussian', 'spherical_uniform'):
+        o, _, _ = sample_camera_positions('cpu', n=4, r=1.5, mode=mode)
+        assert torch.allclose(o.norm(dim=-1), torch.full((4,), 1.5), atol=1e-5)
+
+
+def test_setup_filter_matches_oracle():
+    from ide3d_b200.torch_utils.ops import upfirdn2d as up
+    from oracle import ops as oops
+    for taps, kw in (([1, 3, 3, 1], {}), ([1, 2, 1], dict(gain=4)), (list(range(1, 13)), {}), ([[1, 2], [3, 4]], dict(flip_filter=True)), (None, {})):
+        assert torch.equal(up.setup_filter(taps, **kw), oops.setup_filter(taps, **kw))
