@@ -16,6 +16,7 @@ OK, UNSUPPORTED, INVALID, CUDA_ERROR = 0, -1, -2, -3
 F32, F16, F64 = 0, 1, 2
 JITTER_NONE, JITTER_TENSOR, JITTER_HASH = 0, 1, 2
 CLAMP_SOFTPLUS, CLAMP_RELU = 0, 1
+PRECISION = {'auto': 0, 'fp32': 1, 'tc': 2}
 
 _DTYPES = {torch.float32: F32, torch.float16: F16, torch.float64: F64}
 
@@ -75,7 +76,7 @@ class RaymarchParams(C.Structure):
                 ('jitter_mode', C.c_int), ('jitter_u', C.c_void_p), ('jitter_seed', C.c_uint64),
                 ('clamp_mode', C.c_int), ('last_back', C.c_int), ('white_back', C.c_int), ('max_depth', C.c_float),
                 ('fill_weight', C.c_int), ('noise_std', C.c_float), ('noise', C.c_void_p),
-                ('out_feat', C.c_void_p), ('out_depth', C.c_void_p), ('out_weights', C.c_void_p)]
+                ('out_feat', C.c_void_p), ('out_depth', C.c_void_p), ('out_weights', C.c_void_p), ('precision', C.c_int)]
 
 
 _lib = None

@@ -189,6 +189,8 @@ static int launch_raymarch(const RayArgs& a, cudaStream_t st) {
     return IDE3D_OK;
 }
 
+int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaStream_t st);   // raymarch_tc.cu
+
 }  // namespace ide3d
 
 using namespace ide3d;
@@ -219,6 +221,12 @@ extern "C" int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t
     IDE3D_REQUIRE(p->jitter_mode != IDE3D_JITTER_TENSOR || p->jitter_u, "raymarch: jitter tensor missing");
     IDE3D_REQUIRE((long long)p->n * p->res_w * p->res_h * p->num_steps < (1ll << 32),
                   "raymarch: more than 2^32 samples per call");
+    IDE3D_REQUIRE(p->precision >= IDE3D_PRECISION_AUTO && p->precision <= IDE3D_PRECISION_TC, "raymarch: bad precision");
+    const bool planes_cl = is_channels_last(p->tex) && is_channels_last(p->seg);
+    if (p->precision != IDE3D_PRECISION_FP32) {
+        const int rc_tc = launch_raymarch_tc(p, planes_cl, (cudaStream_t)stream);
+        if (rc_tc != IDE3D_UNSUPPORTED || p->precision == IDE3D_PRECISION_TC) return rc_tc;
+    }
     const int kind = classify_decoder(p->dec);
     if (kind == kDecoderNone) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch: no fused kernel for this decoder shape");
 
@@ -235,7 +243,7 @@ extern "C" int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t
     a.noise_std = p->noise_std; a.noise = (p->noise_std != 0.f) ? p->noise : nullptr;
     a.out_feat = p->out_feat; a.out_depth = p->out_depth; a.out_weights = p->out_weights;
     a.tiles_x = ceil_div(p->res_w, kTileX); a.tiles_y = ceil_div(p->res_h, kTileY);
-    const bool cl = is_channels_last(p->tex) && is_channels_last(p->seg);
+    const bool cl = planes_cl;
     cudaStream_t st = (cudaStream_t)stream;
     switch (kind) {
         case kDense64: return cl ? launch_raymarch<kDense64, true>(a, st) : launch_raymarch<kDense64, false>(a, st);

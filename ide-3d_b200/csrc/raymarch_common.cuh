@@ -84,9 +84,11 @@ __device__ __forceinline__ Foot footprint(float u, float v, int W, int H) {
 // Gather the features of the 32 samples of this warp's chunk from both tri-planes into the staging
 // rows: stage[s*kRow + 0..31] = texture features, stage[s*kRow + 32..63] = shape features.
 // (cx,cy,cz): this lane's own sample in plane grid units.  Inactive lanes pass any finite value.
-template <bool kChannelsLast>
-__device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneView& seg, int n, float cx,
-                                             float cy, float cz, float* __restrict__ stage, int lane) {
+// `store(sample, q, at, as)` receives, for sample `sample` (0..31 of the chunk), the texture / shape features of
+// channels 4q..4q+3.
+template <bool kChannelsLast, typename Store>
+__device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const PlaneView& seg, int n, float cx,
+                                                float cy, float cz, int lane, Store store) {
     const int W = tex.w, H = tex.h;
     // plane 0 samples (x,y), plane 1 (y,z), plane 2 (x,z)   (dnnlib/util.py:589-596)
     const Foot f0 = footprint(cx, cy, W, H);
@@ -139,10 +141,19 @@ __device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneVi
 #pragma unroll
             for (int j = 0; j < 4; ++j) { at[j] += pt[j]; as[j] += ps[j]; }
         }
+        store(src, q, at, as);
+    }
+}
+
+// staging-row flavour used by the SIMT kernels: stage[s*kRow + 0..31] = texture, [32..63] = shape features
+template <bool kChannelsLast>
+__device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneView& seg, int n, float cx,
+                                             float cy, float cz, float* __restrict__ stage, int lane) {
+    gather_chunk_to<kChannelsLast>(tex, seg, n, cx, cy, cz, lane, [stage](int src, int q, const float (&at)[4], const float (&as)[4]) {
         float* row = stage + src * kRow;
         *reinterpret_cast<float4*>(row + q * 4) = make_float4(at[0], at[1], at[2], at[3]);
         *reinterpret_cast<float4*>(row + kFeat + q * 4) = make_float4(as[0], as[1], as[2], as[3]);
-    }
+    });
     __syncwarp();
 }
 

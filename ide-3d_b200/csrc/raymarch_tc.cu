@@ -1,0 +1,412 @@
+// Fused volume renderer, tensor-core decoder: the same chain as raymarch.cu (rays -> jitter -> cam2world -> 2x tri-plane
+// gather -> decoder MLP -> alpha compositing) with the per-sample MLP executed as tcgen05.mma tiles.
+//
+//   tile   = 128 samples (M = 128): 4 warps x 32 consecutive samples of 4 neighbouring rays (2x2 pixels)
+//   A      = gathered features [128 x 64] (texture 0..31 | shape 32..63), bf16 hi + lo, K-major, 128B-swizzled smem rows
+//   layer 1: D1[128 x 64] = A . W1_blk^T      accumulators in TMEM (fp32)
+//   epilog : tcgen05.ld D1 -> + b1 -> softplus -> bf16 hi + lo -> A2 [128 x 64] in smem
+//   layer 2: D2[128 x n]  (+)= A2 . W2_blk^T  for the output-column range the block feeds
+//   final  : tcgen05.ld D2 -> + b2 -> sigma -> warp product scan -> weighted accumulation in registers
+// The decoder is processed in hidden blocks of 64 units (three-head decoder: one block per head; dense decoders: HID/64
+// blocks).  Zero blocks of W1 (a head reads only the texture or only the shape half) and of W2 (a head feeds only its
+// own output columns) are skipped by construction of the MMA program.
+//
+// Precision: every product is evaluated as hi*hi + hi*lo + lo*hi with bf16 operands and fp32 accumulation ("bf16x3"):
+// operands carry 16 mantissa bits, the dropped lo*lo term is 2^-16 relative.  Measured against the fp32 oracle in
+// tests/test_gpu_renderer.py (tolerance stated there).
+//
+// One CTA per SM (256 threads = 2 independent groups of 4 warps sharing one copy of the weights in shared memory), so
+// that the gather of one group overlaps the MMAs / epilogues of the other.
+#include "raymarch_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace ide3d {
+
+constexpr int kTcGroups = 2;
+constexpr int kTcGroupThreads = 128;
+constexpr int kTcThreads = kTcGroups * kTcGroupThreads;
+constexpr int kTcMaxBlocks = 3;
+constexpr int kTileBytes = 128 * 128;                         // [128 rows x 64 bf16]
+constexpr int kWTileBytes = 64 * 128;                         // [64 rows x 64 bf16]
+constexpr int kTmemCols = 256;                                // 2 groups x (D1 64 + D2 64)
+
+// ---- shared memory map (bytes) ----
+constexpr int kSmW = 0;                                       // per block: W1 hi, W1 lo, W2 hi, W2 lo (8 KB each)
+constexpr int kSmGroup = kSmW + kTcMaxBlocks * 4 * kWTileBytes;             // 98304
+constexpr int kSmGroupBytes = 4 * kTileBytes;                                // A hi, A lo, A2 hi, A2 lo
+constexpr int kSmMisc = kSmGroup + kTcGroups * kSmGroupBytes;               // 229376
+constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64) * 4 + 64;             // b1[192], b2[64], mbar[2], tmem ptr
+constexpr int kTcSmemBytes = kSmMisc + kSmMiscBytes + 1024;                 // + slack for the 1024-byte alignment
+
+struct TcRun { int n0, n, accum; };
+struct TcBlock {
+    const float* w1; int w1_ld, k0, kcount;        // W1 rows of this hidden block; inputs land at A columns [k0, k0+kcount)
+    const float* b1;
+    const float* w2; int w2_ld, out0, outc;        // W2[out, hidden cols of this block]; rows feed outputs [out0, out0+outc)
+    int nruns;
+    TcRun runs[4];                                 // layer-2 MMAs: D2 columns [n0, n0+n), accumulate or overwrite
+};
+struct TcProgram {
+    int nblocks;
+    TcBlock blk[kTcMaxBlocks];
+    unsigned written;                              // bit g: D2 columns [16g, 16g+16) are produced by some block
+};
+
+struct TcArgs {
+    PlaneView tex, seg;
+    ide3d_decoder dec;
+    TcProgram prog;
+    const float* cam2world;
+    int n, res_w, res_h, steps;
+    float cam_z, ray_start, ray_end, box_scale;
+    int jitter_mode;
+    const float* jitter_u;
+    uint32_t seed_lo, seed_hi;
+    int clamp_mode, last_back, white_back, fill_weight;
+    float max_depth, noise_std;
+    const float* noise;
+    float *out_feat, *out_depth, *out_weights;
+    int tiles_x, tiles_y;
+};
+
+// write element (row, k) of a [rows x 64] bf16 swizzle-128B tile
+__device__ __forceinline__ void tile_store_bf16(unsigned char* tile, int row, int k, __nv_bfloat16 v) {
+    *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, k >> 3) + (k & 7) * 2) = v;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs a) {
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* b1s = reinterpret_cast<float*>(smem + kSmMisc);
+    float* b2s = b1s + kTcMaxBlocks * 64;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(b2s + 64);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kTcGroups);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = warp >> 2, wg = warp & 3;                    // group, warp within group
+    const TcProgram& P = a.prog;
+
+    // ---------------- one-time setup: weights -> bf16 hi/lo swizzled tiles, biases, barriers, TMEM
+    for (int i = tid; i < P.nblocks * 64 * 64; i += kTcThreads) {
+        const int b = i >> 12, j = (i >> 6) & 63, k = i & 63;
+        const TcBlock& B = P.blk[b];
+        unsigned char* base = smem + kSmW + b * 4 * kWTileBytes;
+        const float v1 = (k >= B.k0 && k < B.k0 + B.kcount) ? B.w1[j * B.w1_ld + (k - B.k0)] : 0.f;   // W1[hidden j][input k]
+        const float v2 = (j >= B.out0 && j < B.out0 + B.outc) ? B.w2[(j - B.out0) * B.w2_ld + k] : 0.f; // W2[output j][hidden k]
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(v1, hi, lo);
+        tile_store_bf16(base, j, k, hi);
+        tile_store_bf16(base + kWTileBytes, j, k, lo);
+        tc::split_bf16(v2, hi, lo);
+        tile_store_bf16(base + 2 * kWTileBytes, j, k, hi);
+        tile_store_bf16(base + 3 * kWTileBytes, j, k, lo);
+    }
+    for (int i = tid; i < kTcMaxBlocks * 64; i += kTcThreads) b1s[i] = (i < P.nblocks * 64) ? P.blk[i >> 6].b1[i & 63] : 0.f;
+    if (tid < 64) {
+        float v = 0.f;
+        for (int h = 0; h < a.dec.num_heads; ++h) {
+            const ide3d_mlp_head& H = a.dec.heads[h];
+            if (tid >= H.out_offset && tid < H.out_offset + H.out_count) v = H.b2[tid - H.out_offset];
+        }
+        b2s[tid] = v;
+    }
+    if (tid == 0) {
+        for (int i = 0; i < kTcGroups; ++i) tc::mbar_init(&mbar[i], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
+    tc::fence_async_smem();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t d1_col = tmem_base + g * 128;
+    const uint32_t d2_col = d1_col + 64;
+    const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;        // this warp's TMEM lanes
+
+    unsigned char* grp = smem + kSmGroup + g * kSmGroupBytes;
+    unsigned char* a_hi = grp;
+    unsigned char* a_lo = grp + kTileBytes;
+    unsigned char* a2_hi = grp + 2 * kTileBytes;
+    unsigned char* a2_lo = grp + 3 * kTileBytes;
+    const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo);
+    const uint32_t a2_hi_u = tc::smem_u32(a2_hi), a2_lo_u = tc::smem_u32(a2_lo);
+    const uint32_t w_u = tc::smem_u32(smem + kSmW);
+    const bool issuer = (wg == 0 && lane == 0);
+    uint32_t parity = 0;
+
+    // layer-1 MMAs of hidden block b: D1 = A[:, k-range] . W1_b[:, k-range]^T      (hi*hi + hi*lo + lo*hi)
+    auto issue_l1 = [&](int b) {
+        const TcBlock& B = P.blk[b];
+        const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+        const uint32_t w1hi = w_u + b * 4 * kWTileBytes, w1lo = w1hi + kWTileBytes;
+        const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
+        for (int ks = 0; ks < ksn; ++ks) {
+            const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K
+            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
+            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
+            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
+        }
+    };
+    // layer-2 MMAs of hidden block b: D2[:, n0:n0+n] (+)= A2 . W2_b[n0:n0+n, :]^T
+    auto issue_l2 = [&](int b) {
+        const TcBlock& B = P.blk[b];
+        const uint32_t w2hi = w_u + b * 4 * kWTileBytes + 2 * kWTileBytes, w2lo = w2hi + kWTileBytes;
+        for (int r = 0; r < B.nruns; ++r) {
+            const TcRun& R = B.runs[r];
+            const uint32_t idesc = tc::make_idesc_bf16(128, R.n);
+            const uint32_t rowoff = (uint32_t)R.n0 * 128;                    // n0 is a multiple of 16 -> atom aligned
+            for (int ks = 0; ks < 4; ++ks) {
+                const uint32_t off = (uint32_t)ks * 32;
+                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, (R.accum || ks > 0));
+                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2lo + rowoff + off), idesc, 1);
+                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_lo_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, 1);
+            }
+        }
+    };
+
+    const int R = a.res_w * a.res_h, S = a.steps;
+    const int tiles_per_frame = a.tiles_x * a.tiles_y;
+    const int num_tiles = tiles_per_frame * a.n;
+    const int chunks = (S + 31) >> 5;
+    const int row = wg * 32 + lane;                              // this thread's row of the tile in the MLP phases
+
+    for (int tile = blockIdx.x * kTcGroups + g; tile < num_tiles; tile += gridDim.x * kTcGroups) {
+        const int n = tile / tiles_per_frame;
+        const int t = tile - n * tiles_per_frame;
+        const int px = (t % a.tiles_x) * 2 + (wg & 1);
+        const int py = (t / a.tiles_x) * 2 + (wg >> 1);
+        const bool ray_ok = (px < a.res_w) && (py < a.res_h);        // warp-uniform; dead warps still join the barriers
+        const int ray = ray_ok ? py * a.res_w + px : 0;
+
+        const float x = linspace_at(-1.f, 1.f, a.res_w, px);
+        const float y = linspace_at(1.f, -1.f, a.res_h, py);
+        const float inv = 1.f / sqrtf(x * x + y * y + a.cam_z * a.cam_z);
+        const float dx = x * inv, dy = y * inv, dz = a.cam_z * inv;
+        const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
+        const float* M = a.cam2world + n * 16;
+        const float m00 = M[0], m01 = M[1], m02 = M[2], m03 = M[3];
+        const float m10 = M[4], m11 = M[5], m12 = M[6], m13 = M[7];
+        const float m20 = M[8], m21 = M[9], m22 = M[10], m23 = M[11];
+        const float spacing = (S > 1) ? linspace_at(a.ray_start, a.ray_end, S, 1) - linspace_at(a.ray_start, a.ray_end, S, 0) : 0.f;
+        const long long sample_base = ((long long)n * R + ray) * S;
+
+        float acc[kOut - 1];
+#pragma unroll
+        for (int c = 0; c < kOut - 1; ++c) acc[c] = 0.f;
+        float acc_w = 0.f, acc_d = 0.f, carry = 1.f;
+
+        for (int ch = 0; ch < chunks; ++ch) {
+            const int s = ch * 32 + lane;
+            const bool live = ray_ok && (s < S);
+            float z0 = 0.f, z1 = 0.f, off0 = 0.f;
+            if (live) {
+                z0 = linspace_at(a.ray_start, a.ray_end, S, s);
+                z1 = (s + 1 < S) ? linspace_at(a.ray_start, a.ray_end, S, s + 1) : 0.f;
+                if (a.jitter_mode == IDE3D_JITTER_TENSOR) {
+                    off0 = (a.jitter_u[sample_base + s] - 0.5f) * spacing;
+                    if (s + 1 < S) z1 += (a.jitter_u[sample_base + s + 1] - 0.5f) * spacing;
+                } else if (a.jitter_mode == IDE3D_JITTER_HASH) {
+                    const uint32_t gi = (uint32_t)(sample_base + s);
+                    off0 = (jitter_hash(gi, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
+                    if (s + 1 < S) z1 += (jitter_hash(gi + 1u, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
+                }
+            }
+            const float zj = z0 + off0;
+            const float pcx = dx * z0 + off0 * dx, pcy = dy * z0 + off0 * dy, pcz = dz * z0 + off0 * dz;
+            float cx = (m00 * pcx + m01 * pcy + m02 * pcz + m03) * a.box_scale;
+            float cy = (m10 * pcx + m11 * pcy + m12 * pcz + m13) * a.box_scale;
+            float cz = (m20 * pcx + m21 * pcy + m22 * pcz + m23) * a.box_scale;
+            if (!live) { cx = cy = cz = 4.f; }
+
+            // ---- gather -> A (bf16 hi / lo), row = wg*32 + sample
+            gather_chunk_to<true>(a.tex, a.seg, n, cx, cy, cz, lane,
+                                  [&](int src, int q, const float (&at)[4], const float (&as)[4]) {
+                                      const int r = wg * 32 + src;
+                                      __nv_bfloat16 h[4], l[4];
+#pragma unroll
+                                      for (int j = 0; j < 4; ++j) tc::split_bf16(at[j], h[j], l[j]);
+                                      uint32_t o = tc::sw128_offset(r, q >> 1) + (q & 1) * 8;
+                                      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
+                                      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
+#pragma unroll
+                                      for (int j = 0; j < 4; ++j) tc::split_bf16(as[j], h[j], l[j]);
+                                      o = tc::sw128_offset(r, 4 + (q >> 1)) + (q & 1) * 8;
+                                      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
+                                      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
+                                  });
+            tc::fence_async_smem();
+            tc::tc_fence_before();
+            tc::bar_sync(1 + g, kTcGroupThreads);
+
+            // ---- hidden blocks: L1(b) [+ L2(b-1)] -> softplus epilogue -> A2
+            for (int b = 0; b < P.nblocks; ++b) {
+                if (issuer) {
+                    tc::tc_fence_after();
+                    if (b > 0) issue_l2(b - 1);
+                    issue_l1(b);
+                    tc::umma_commit(&mbar[g]);
+                }
+                tc::mbar_wait(&mbar[g], parity);
+                parity ^= 1;
+                tc::tc_fence_after();
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float v[32];
+                    tc::tmem_ld32(d1_col + lane_sel + half * 32, v);
+                    const float* bb = b1s + b * 64 + half * 32;
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
+                        uint32_t ph[4], pl[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float h0 = softplus_fast(v[c8 * 8 + 2 * j] + bb[c8 * 8 + 2 * j]);
+                            const float h1 = softplus_fast(v[c8 * 8 + 2 * j + 1] + bb[c8 * 8 + 2 * j + 1]);
+                            __nv_bfloat16 h0h, h0l, h1h, h1l;
+                            tc::split_bf16(h0, h0h, h0l);
+                            tc::split_bf16(h1, h1h, h1l);
+                            ph[j] = tc::pack_bf16(h0h, h1h);
+                            pl[j] = tc::pack_bf16(h0l, h1l);
+                        }
+                        const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
+                        *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                        *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    }
+                }
+                tc::fence_async_smem();
+                tc::tc_fence_before();
+                tc::bar_sync(1 + g, kTcGroupThreads);
+            }
+            if (issuer) {
+                tc::tc_fence_after();
+                issue_l2(P.nblocks - 1);
+                tc::umma_commit(&mbar[g]);
+            }
+            tc::mbar_wait(&mbar[g], parity);
+            parity ^= 1;
+            tc::tc_fence_after();
+
+            // ---- outputs: columns 32..63 first (semantic logits 32..50, sigma 51), then the colour features 0..31
+            float hi32[32];
+            tc::tmem_ld32(d2_col + lane_sel + 32, hi32);
+            float sigma = ((P.written >> 3) & 1u) ? hi32[19] + b2s[51] : b2s[51];
+            if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[sample_base + s];
+            const float delta = (s + 1 < S) ? (z1 - zj) * dnorm : 1e10f;
+            const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
+            const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
+            const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
+            float total;
+            const float T = warp_exclusive_product(keep, lane, total) * carry;
+            carry *= total;
+            float w = alpha * T;
+            acc_w += w;
+            if (a.last_back && ch == chunks - 1) {
+                const float wsum_all = warp_sum(acc_w);
+                if (s == S - 1) w += 1.f - wsum_all;
+            }
+            if (a.out_weights != nullptr && live) a.out_weights[sample_base + s] = w;
+            acc_d = fmaf(w, zj, acc_d);
+#pragma unroll
+            for (int c = 0; c < 19; ++c) {
+                const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? hi32[c] : 0.f) + b2s[32 + c];
+                acc[32 + c] = fmaf(w, v, acc[32 + c]);
+            }
+            float lo32[32];
+            tc::tmem_ld32(d2_col + lane_sel, lo32);
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+                const float v = (((P.written >> (c >> 4)) & 1u) ? lo32[c] : 0.f) + b2s[c];
+                acc[c] = fmaf(w, v, acc[c]);
+            }
+            tc::tc_fence_before();        // TMEM reads of this chunk are ordered before the next chunk's MMAs (next bar_sync)
+        }
+
+        // ---- per-ray reduction and store (identical to the SIMT kernel)
+        const float wsum = warp_sum(acc_w);
+        float depth = warp_sum(acc_d);
+        float mine0 = 0.f, mine1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < kOut - 1; ++c) {
+            const float v = warp_sum(acc[c]);
+            if (c == lane) mine0 = v;
+            if (c == lane + 32) mine1 = v;
+        }
+        if (a.white_back) { mine0 += 1.f - wsum; mine1 += 1.f - wsum; }
+        if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
+        if (a.fill_weight) { mine0 = wsum; mine1 = wsum; }
+        if (ray_ok) {
+            float* of = a.out_feat + ((long long)n * R + ray) * (kOut - 1);
+            of[lane] = mine0;
+            if (lane + 32 < kOut - 1) of[lane + 32] = mine1;
+            if (lane == 0) a.out_depth[(long long)n * R + ray] = depth;
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// Build the hidden-block program from the head list.  Returns false when the decoder does not fit
+// (hidden not a multiple of 64, more than kTcMaxBlocks blocks, outputs beyond 64 columns).
+static bool build_program(const ide3d_decoder& d, TcProgram& P) {
+    P.nblocks = 0;
+    P.written = 0;
+    for (int h = 0; h < d.num_heads; ++h) {
+        const ide3d_mlp_head& H = d.heads[h];
+        if (H.hidden <= 0 || H.hidden % 64 != 0) return false;
+        if (H.out_offset < 0 || H.out_count <= 0 || H.out_offset + H.out_count > 64) return false;
+        if (H.in_sel < 0 || H.in_sel > 2) return false;
+        const int in = (H.in_sel == 2) ? 64 : 32;
+        for (int c = 0; c < H.hidden / 64; ++c) {
+            if (P.nblocks == kTcMaxBlocks) return false;
+            TcBlock& B = P.blk[P.nblocks++];
+            B.w1 = H.w1 + (size_t)c * 64 * in; B.w1_ld = in;
+            B.k0 = (H.in_sel == 1) ? 32 : 0; B.kcount = in;
+            B.b1 = H.b1 + c * 64;
+            B.w2 = H.w2 + c * 64; B.w2_ld = H.hidden;
+            B.out0 = H.out_offset; B.outc = H.out_count;
+            // layer-2 column range in units of 16, split into runs of equal "already written" status
+            const int g0 = H.out_offset / 16, g1 = (H.out_offset + H.out_count + 15) / 16;
+            B.nruns = 0;
+            int gi = g0;
+            while (gi < g1) {
+                const int st = (P.written >> gi) & 1;
+                int ge = gi + 1;
+                while (ge < g1 && (int)((P.written >> ge) & 1) == st) ++ge;
+                B.runs[B.nruns++] = TcRun{gi * 16, (ge - gi) * 16, st};
+                gi = ge;
+            }
+            for (int q = g0; q < g1; ++q) P.written |= 1u << q;
+        }
+    }
+    return P.nblocks > 0;
+}
+
+// entry used by ide3d_raymarch_fwd (raymarch.cu); IDE3D_UNSUPPORTED when this decoder / layout has no TC kernel
+int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaStream_t st) {
+    if (!channels_last) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: planes must be channels-last");
+    TcArgs a;
+    if (!build_program(p->dec, a.prog)) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: decoder shape not supported");
+    a.tex = make_view(p->tex); a.seg = make_view(p->seg); a.dec = p->dec;
+    a.cam2world = p->cam2world;
+    a.n = p->n; a.res_w = p->res_w; a.res_h = p->res_h; a.steps = p->num_steps;
+    a.cam_z = (float)(-1.0 / tan((2.0 * 3.14159265358979323846 * (double)p->fov_deg / 360.0) / 2.0));
+    a.ray_start = p->ray_start; a.ray_end = p->ray_end; a.box_scale = p->box_scale;
+    a.jitter_mode = p->jitter_mode; a.jitter_u = p->jitter_u;
+    a.seed_lo = (uint32_t)(p->jitter_seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->jitter_seed >> 32);
+    a.clamp_mode = p->clamp_mode; a.last_back = p->last_back; a.white_back = p->white_back;
+    a.fill_weight = p->fill_weight; a.max_depth = p->max_depth;
+    a.noise_std = p->noise_std; a.noise = (p->noise_std != 0.f) ? p->noise : nullptr;
+    a.out_feat = p->out_feat; a.out_depth = p->out_depth; a.out_weights = p->out_weights;
+    a.tiles_x = ceil_div(p->res_w, 2); a.tiles_y = ceil_div(p->res_h, 2);
+    IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    const int num_tiles = a.tiles_x * a.tiles_y * a.n;
+    int grid = sm_count();
+    if (grid > ceil_div(num_tiles, kTcGroups)) grid = ceil_div(num_tiles, kTcGroups);
+    raymarch_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    IDE3D_CHECK_LAUNCH("raymarch_tc_kernel");
+    return IDE3D_OK;
+}
+
+}  // namespace ide3d

@@ -63,9 +63,10 @@ def _decoder(dec, device):
 def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, fov=18.0, ray_start=2.25,
              ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
              clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None,
-             return_weights=False, convert_layout=True):
+             return_weights=False, convert_layout=True, precision='auto'):
     """Fused render of N frames.  -> feat [N,R,51], depth [N,R,1], weights [N,R,S,1] | None.
-    jitter_u: explicit uniforms [N,R,S]; jitter_seed: in-kernel counter hash; neither: no jitter."""
+    jitter_u: explicit uniforms [N,R,S]; jitter_seed: in-kernel counter hash; neither: no jitter.
+    precision: 'auto' | 'fp32' (CUDA-core FFMA decoder) | 'tc' (tcgen05 decoder, bf16x3 products)."""
     if clamp_mode not in ('softplus', 'relu'):
         raise ValueError('Need to choose clamp mode')
     if fill_mode not in (None, 'weight'):
@@ -101,6 +102,7 @@ def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), nu
     p.last_back, p.white_back = int(bool(last_back)), int(bool(white_back))
     p.max_depth, p.fill_weight = float(max_depth or 0.0), int(fill_mode == 'weight')
     p.out_feat, p.out_depth, p.out_weights = L.ptr(feat), L.ptr(depth), L.ptr(weights)
+    p.precision = L.PRECISION[precision]
     with torch.cuda.device(dev):
         if kernel_events is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

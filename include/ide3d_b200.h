@@ -166,6 +166,10 @@ typedef struct ide3d_decoder {
 
 enum ide3d_jitter { IDE3D_JITTER_NONE = 0, IDE3D_JITTER_TENSOR = 1, IDE3D_JITTER_HASH = 2 };
 enum ide3d_clamp { IDE3D_CLAMP_SOFTPLUS = 0, IDE3D_CLAMP_RELU = 1 };
+/* AUTO: tensor cores when the decoder / layout allows, else CUDA cores.  FP32: CUDA-core FFMA, plain fp32.
+ * TC: tcgen05 tensor cores, every product as bf16 hi*hi + hi*lo + lo*hi with fp32 accumulation (16-bit operand
+ * mantissas); IDE3D_UNSUPPORTED if the decoder shape or plane layout has no tensor-core kernel. */
+enum ide3d_precision { IDE3D_PRECISION_AUTO = 0, IDE3D_PRECISION_FP32 = 1, IDE3D_PRECISION_TC = 2 };
 
 typedef struct ide3d_raymarch_params {
     ide3d_triplane tex, seg;
@@ -188,6 +192,7 @@ typedef struct ide3d_raymarch_params {
     float* out_feat;            /* [N, R, 51]  composited colour features + semantic logits */
     float* out_depth;           /* [N, R] */
     float* out_weights;         /* [N, R, S] or NULL */
+    int precision;              /* ide3d_precision: how the decoder MLP is evaluated */
 } ide3d_raymarch_params;
 int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t stream);
 
