@@ -154,6 +154,8 @@ def cpu_reference_fps(G_cpu, ws1, c1, reps):
 
 def build_generator(device):
     from ide3d_b200.compat import random_init_generator
+    from ide3d_b200.torch_utils import custom_ops
+    custom_ops.verbosity = 'none'
     return random_init_generator(device=device, seed=0)
 
 
@@ -204,6 +206,8 @@ def main():
         return
 
     from ide3d_b200 import _lib, dist as idist, render
+    from ide3d_b200.torch_utils import custom_ops
+    custom_ops.verbosity = 'none'            # keep stdout to the one JSON line
     rank, world, device = idist.init_from_env()
     assert device.type == 'cuda', 'bench.py needs a CUDA device (the product has no CPU path)'
     assert world == args.gpus or world == 1, f'--gpus {args.gpus} but WORLD_SIZE={world}'

@@ -1,7 +1,7 @@
 // Fused volume renderer, tensor-core decoder: the same chain as raymarch.cu (rays -> jitter -> cam2world -> 2x tri-plane
 // gather -> decoder MLP -> alpha compositing) with the per-sample MLP executed as tcgen05.mma tiles.
 //
-//   tile   = 128 samples (M = 128): 4 warps x 32 consecutive samples of 4 neighbouring rays (2x2 pixels)
+//   tile   = 128 samples (M = 128): 4 x 32 consecutive samples of 4 neighbouring rays (2x2 pixels)
 //   A      = gathered features [128 x 64] (texture 0..31 | shape 32..63), bf16 hi + lo, K-major, 128B-swizzled smem rows
 //   layer 1: D1[128 x 64] = A . W1_blk^T      accumulators in TMEM (fp32)
 //   epilog : tcgen05.ld D1 -> + b1 -> softplus -> bf16 hi + lo -> A2 [128 x 64] in smem
@@ -15,27 +15,32 @@
 // operands carry 16 mantissa bits, the dropped lo*lo term is 2^-16 relative.  Measured against the fp32 oracle in
 // tests/test_gpu_renderer.py (tolerance stated there).
 //
-// One CTA per SM (256 threads = 2 independent groups of 4 warps sharing one copy of the weights in shared memory), so
-// that the gather of one group overlaps the MMAs / epilogues of the other.
+// Warp-specialised, one persistent CTA per SM (384 threads):
+//   warpgroup 0 (4 warps)  consumer: waits for a full A stage, issues the UMMAs (one elected thread), runs the softplus and
+//                          compositing epilogues out of TMEM, owns the per-ray accumulators (232 registers/thread)
+//   warpgroups 1-2 (8 warps) producers: compute sample positions and gather features into a 3-stage ring of A tiles
+//                          (104 registers/thread, many loads in flight); mbarrier full/empty hand-off, the "empty" arrive is
+//                          the tcgen05.commit of the last MMA that reads the stage.
 #include "raymarch_common.cuh"
 #include "tc_ptx.cuh"
 
 namespace ide3d {
 
-constexpr int kTcGroups = 2;
-constexpr int kTcGroupThreads = 128;
-constexpr int kTcThreads = kTcGroups * kTcGroupThreads;
+constexpr int kTcConsumerThreads = 128;
+constexpr int kTcProducerWarps = 8;
+constexpr int kTcThreads = kTcConsumerThreads + kTcProducerWarps * 32;
+constexpr int kTcStages = 3;
 constexpr int kTcMaxBlocks = 3;
 constexpr int kTileBytes = 128 * 128;                         // [128 rows x 64 bf16]
 constexpr int kWTileBytes = 64 * 128;                         // [64 rows x 64 bf16]
-constexpr int kTmemCols = 256;                                // 2 groups x (D1 64 + D2 64)
+constexpr int kTmemCols = 128;                                // D1 64 + D2 64
 
 // ---- shared memory map (bytes) ----
 constexpr int kSmW = 0;                                       // per block: W1 hi, W1 lo, W2 hi, W2 lo (8 KB each)
-constexpr int kSmGroup = kSmW + kTcMaxBlocks * 4 * kWTileBytes;             // 98304
-constexpr int kSmGroupBytes = 4 * kTileBytes;                                // A hi, A lo, A2 hi, A2 lo
-constexpr int kSmMisc = kSmGroup + kTcGroups * kSmGroupBytes;               // 229376
-constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64) * 4 + 64;             // b1[192], b2[64], mbar[2], tmem ptr
+constexpr int kSmA2 = kSmW + kTcMaxBlocks * 4 * kWTileBytes;                // 98304: A2 hi, A2 lo
+constexpr int kSmStage = kSmA2 + 2 * kTileBytes;                             // 131072: kTcStages x (A hi, A lo)
+constexpr int kSmMisc = kSmStage + kTcStages * 2 * kTileBytes;              // 229376
+constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64) * 4 + 128;            // b1[192], b2[64], mbarriers, tmem ptr
 constexpr int kTcSmemBytes = kSmMisc + kSmMiscBytes + 1024;                 // + slack for the 1024-byte alignment
 
 struct TcRun { int n0, n, accum; };
@@ -74,16 +79,64 @@ __device__ __forceinline__ void tile_store_bf16(unsigned char* tile, int row, in
     *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, k >> 3) + (k & 7) * 2) = v;
 }
 
+// per-ray constants shared by producer and consumer code
+struct RaySetup {
+    int n, ray;
+    bool ok;
+    float dx, dy, dz, dnorm, spacing;
+    float m00, m01, m02, m03, m10, m11, m12, m13, m20, m21, m22, m23;
+    long long sample_base;
+};
+__device__ __forceinline__ RaySetup ray_setup(const TcArgs& a, int ptile, int quarter) {
+    RaySetup r;
+    const int tiles_per_frame = a.tiles_x * a.tiles_y;
+    r.n = ptile / tiles_per_frame;
+    const int t = ptile - r.n * tiles_per_frame;
+    const int px = (t % a.tiles_x) * 2 + (quarter & 1);
+    const int py = (t / a.tiles_x) * 2 + (quarter >> 1);
+    r.ok = (px < a.res_w) && (py < a.res_h);
+    r.ray = r.ok ? py * a.res_w + px : 0;
+    const float x = linspace_at(-1.f, 1.f, a.res_w, px);
+    const float y = linspace_at(1.f, -1.f, a.res_h, py);
+    const float inv = 1.f / sqrtf(x * x + y * y + a.cam_z * a.cam_z);
+    r.dx = x * inv; r.dy = y * inv; r.dz = a.cam_z * inv;
+    r.dnorm = sqrtf(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+    const float* M = a.cam2world + r.n * 16;
+    r.m00 = M[0]; r.m01 = M[1]; r.m02 = M[2]; r.m03 = M[3];
+    r.m10 = M[4]; r.m11 = M[5]; r.m12 = M[6]; r.m13 = M[7];
+    r.m20 = M[8]; r.m21 = M[9]; r.m22 = M[10]; r.m23 = M[11];
+    const int S = a.steps;
+    r.spacing = (S > 1) ? linspace_at(a.ray_start, a.ray_end, S, 1) - linspace_at(a.ray_start, a.ray_end, S, 0) : 0.f;
+    r.sample_base = ((long long)r.n * (a.res_w * a.res_h) + r.ray) * S;
+    return r;
+}
+// jittered depth of sample s and of sample s+1 (z1, only meaningful when s+1 < S), and the jitter offset of s
+__device__ __forceinline__ void sample_depths(const TcArgs& a, const RaySetup& r, int s, float& z0, float& off0, float& z1) {
+    const int S = a.steps;
+    z0 = linspace_at(a.ray_start, a.ray_end, S, s);
+    z1 = (s + 1 < S) ? linspace_at(a.ray_start, a.ray_end, S, s + 1) : 0.f;
+    off0 = 0.f;
+    if (a.jitter_mode == IDE3D_JITTER_TENSOR) {
+        off0 = (a.jitter_u[r.sample_base + s] - 0.5f) * r.spacing;
+        if (s + 1 < S) z1 += (a.jitter_u[r.sample_base + s + 1] - 0.5f) * r.spacing;
+    } else if (a.jitter_mode == IDE3D_JITTER_HASH) {
+        const uint32_t gi = (uint32_t)(r.sample_base + s);
+        off0 = (jitter_hash(gi, a.seed_lo, a.seed_hi) - 0.5f) * r.spacing;
+        if (s + 1 < S) z1 += (jitter_hash(gi + 1u, a.seed_lo, a.seed_hi) - 0.5f) * r.spacing;
+    }
+}
+
 __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs a) {
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* b1s = reinterpret_cast<float*>(smem + kSmMisc);
     float* b2s = b1s + kTcMaxBlocks * 64;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(b2s + 64);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + kTcGroups);
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b2s + 64);        // [kTcStages] producers -> consumer
+    uint64_t* bar_empty = bar_full + kTcStages;                        // [kTcStages] consumer (tcgen05.commit) -> producers
+    uint64_t* bar_mma = bar_empty + kTcStages;                         // consumer-internal: MMA batch done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int g = warp >> 2, wg = warp & 3;                    // group, warp within group
     const TcProgram& P = a.prog;
 
     // ---------------- one-time setup: weights -> bf16 hi/lo swizzled tiles, biases, barriers, TMEM
@@ -111,7 +164,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         b2s[tid] = v;
     }
     if (tid == 0) {
-        for (int i = 0; i < kTcGroups; ++i) tc::mbar_init(&mbar[i], 1);
+        for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(&bar_full[i], 4); tc::mbar_init(&bar_empty[i], 1); }
+        tc::mbar_init(bar_mma, 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
@@ -120,225 +174,221 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
     __syncthreads();
     tc::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t d1_col = tmem_base + g * 128;
-    const uint32_t d2_col = d1_col + 64;
-    const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;        // this warp's TMEM lanes
 
-    unsigned char* grp = smem + kSmGroup + g * kSmGroupBytes;
-    unsigned char* a_hi = grp;
-    unsigned char* a_lo = grp + kTileBytes;
-    unsigned char* a2_hi = grp + 2 * kTileBytes;
-    unsigned char* a2_lo = grp + 3 * kTileBytes;
-    const uint32_t a_hi_u = tc::smem_u32(a_hi), a_lo_u = tc::smem_u32(a_lo);
-    const uint32_t a2_hi_u = tc::smem_u32(a2_hi), a2_lo_u = tc::smem_u32(a2_lo);
-    const uint32_t w_u = tc::smem_u32(smem + kSmW);
-    const bool issuer = (wg == 0 && lane == 0);
-    uint32_t parity = 0;
-
-    // layer-1 MMAs of hidden block b: D1 = A[:, k-range] . W1_b[:, k-range]^T      (hi*hi + hi*lo + lo*hi)
-    auto issue_l1 = [&](int b) {
-        const TcBlock& B = P.blk[b];
-        const uint32_t idesc = tc::make_idesc_bf16(128, 64);
-        const uint32_t w1hi = w_u + b * 4 * kWTileBytes, w1lo = w1hi + kWTileBytes;
-        const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
-        for (int ks = 0; ks < ksn; ++ks) {
-            const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K
-            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
-            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
-            tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
-        }
-    };
-    // layer-2 MMAs of hidden block b: D2[:, n0:n0+n] (+)= A2 . W2_b[n0:n0+n, :]^T
-    auto issue_l2 = [&](int b) {
-        const TcBlock& B = P.blk[b];
-        const uint32_t w2hi = w_u + b * 4 * kWTileBytes + 2 * kWTileBytes, w2lo = w2hi + kWTileBytes;
-        for (int r = 0; r < B.nruns; ++r) {
-            const TcRun& R = B.runs[r];
-            const uint32_t idesc = tc::make_idesc_bf16(128, R.n);
-            const uint32_t rowoff = (uint32_t)R.n0 * 128;                    // n0 is a multiple of 16 -> atom aligned
-            for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t off = (uint32_t)ks * 32;
-                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, (R.accum || ks > 0));
-                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2lo + rowoff + off), idesc, 1);
-                tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_lo_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, 1);
-            }
-        }
-    };
-
-    const int R = a.res_w * a.res_h, S = a.steps;
-    const int tiles_per_frame = a.tiles_x * a.tiles_y;
-    const int num_tiles = tiles_per_frame * a.n;
+    const int S = a.steps;
+    const int num_ptiles = a.tiles_x * a.tiles_y * a.n;
     const int chunks = (S + 31) >> 5;
-    const int row = wg * 32 + lane;                              // this thread's row of the tile in the MLP phases
 
-    for (int tile = blockIdx.x * kTcGroups + g; tile < num_tiles; tile += gridDim.x * kTcGroups) {
-        const int n = tile / tiles_per_frame;
-        const int t = tile - n * tiles_per_frame;
-        const int px = (t % a.tiles_x) * 2 + (wg & 1);
-        const int py = (t / a.tiles_x) * 2 + (wg >> 1);
-        const bool ray_ok = (px < a.res_w) && (py < a.res_h);        // warp-uniform; dead warps still join the barriers
-        const int ray = ray_ok ? py * a.res_w + px : 0;
-
-        const float x = linspace_at(-1.f, 1.f, a.res_w, px);
-        const float y = linspace_at(1.f, -1.f, a.res_h, py);
-        const float inv = 1.f / sqrtf(x * x + y * y + a.cam_z * a.cam_z);
-        const float dx = x * inv, dy = y * inv, dz = a.cam_z * inv;
-        const float dnorm = sqrtf(dx * dx + dy * dy + dz * dz);
-        const float* M = a.cam2world + n * 16;
-        const float m00 = M[0], m01 = M[1], m02 = M[2], m03 = M[3];
-        const float m10 = M[4], m11 = M[5], m12 = M[6], m13 = M[7];
-        const float m20 = M[8], m21 = M[9], m22 = M[10], m23 = M[11];
-        const float spacing = (S > 1) ? linspace_at(a.ray_start, a.ray_end, S, 1) - linspace_at(a.ray_start, a.ray_end, S, 0) : 0.f;
-        const long long sample_base = ((long long)n * R + ray) * S;
-
-        float acc[kOut - 1];
+    if (warp >= 4) {
+        // =========================================================================== producers
+        tc::setmaxnreg_dec<104>();
+        const int pw = warp - 4, pg = pw >> 2, quarter = pw & 3;
+        int q = 0;
+        for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
+            const RaySetup r = ray_setup(a, pt, quarter);
+            for (int ch = 0; ch < chunks; ++ch, ++q) {
+                if ((q & 1) != pg) continue;
+                const int stage = q % kTcStages, use = q / kTcStages;
+                tc::mbar_wait(&bar_empty[stage], (use + 1) & 1);             // first use passes immediately
+                const int s = ch * 32 + lane;
+                const bool live = r.ok && (s < S);
+                float cx = 4.f, cy = 4.f, cz = 4.f;
+                if (live) {
+                    float z0, off0, z1;
+                    sample_depths(a, r, s, z0, off0, z1);
+                    const float pcx = r.dx * z0 + off0 * r.dx, pcy = r.dy * z0 + off0 * r.dy, pcz = r.dz * z0 + off0 * r.dz;
+                    cx = (r.m00 * pcx + r.m01 * pcy + r.m02 * pcz + r.m03) * a.box_scale;
+                    cy = (r.m10 * pcx + r.m11 * pcy + r.m12 * pcz + r.m13) * a.box_scale;
+                    cz = (r.m20 * pcx + r.m21 * pcy + r.m22 * pcz + r.m23) * a.box_scale;
+                }
+                unsigned char* a_hi = smem + kSmStage + stage * 2 * kTileBytes;
+                unsigned char* a_lo = a_hi + kTileBytes;
+                gather_chunk_to<true>(a.tex, a.seg, r.n, cx, cy, cz, lane,
+                                      [&](int src, int qq, const float (&at)[4], const float (&as)[4]) {
+                                          const int row = quarter * 32 + src;
+                                          __nv_bfloat16 h[4], l[4];
 #pragma unroll
-        for (int c = 0; c < kOut - 1; ++c) acc[c] = 0.f;
-        float acc_w = 0.f, acc_d = 0.f, carry = 1.f;
+                                          for (int j = 0; j < 4; ++j) tc::split_bf16(at[j], h[j], l[j]);
+                                          uint32_t o = tc::sw128_offset(row, qq >> 1) + (qq & 1) * 8;
+                                          *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
+                                          *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
+#pragma unroll
+                                          for (int j = 0; j < 4; ++j) tc::split_bf16(as[j], h[j], l[j]);
+                                          o = tc::sw128_offset(row, 4 + (qq >> 1)) + (qq & 1) * 8;
+                                          *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
+                                          *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
+                                      });
+                tc::fence_async_smem();                                      // my generic-proxy stores -> async proxy (UMMA)
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&bar_full[stage]);
+            }
+        }
+    } else {
+        // =========================================================================== consumer
+        tc::setmaxnreg_inc<232>();
+        const int wg = warp;
+        const uint32_t d1_col = tmem_base, d2_col = tmem_base + 64;
+        const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;
+        unsigned char* a2_hi = smem + kSmA2;
+        unsigned char* a2_lo = a2_hi + kTileBytes;
+        const uint32_t a2_hi_u = tc::smem_u32(a2_hi), a2_lo_u = tc::smem_u32(a2_lo);
+        const uint32_t w_u = tc::smem_u32(smem + kSmW);
+        const uint32_t stage_u = tc::smem_u32(smem + kSmStage);
+        const bool issuer = (wg == 0 && lane == 0);
+        const int row = wg * 32 + lane;
+        uint32_t parity = 0;
 
-        for (int ch = 0; ch < chunks; ++ch) {
-            const int s = ch * 32 + lane;
-            const bool live = ray_ok && (s < S);
-            float z0 = 0.f, z1 = 0.f, off0 = 0.f;
-            if (live) {
-                z0 = linspace_at(a.ray_start, a.ray_end, S, s);
-                z1 = (s + 1 < S) ? linspace_at(a.ray_start, a.ray_end, S, s + 1) : 0.f;
-                if (a.jitter_mode == IDE3D_JITTER_TENSOR) {
-                    off0 = (a.jitter_u[sample_base + s] - 0.5f) * spacing;
-                    if (s + 1 < S) z1 += (a.jitter_u[sample_base + s + 1] - 0.5f) * spacing;
-                } else if (a.jitter_mode == IDE3D_JITTER_HASH) {
-                    const uint32_t gi = (uint32_t)(sample_base + s);
-                    off0 = (jitter_hash(gi, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
-                    if (s + 1 < S) z1 += (jitter_hash(gi + 1u, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
+        auto issue_l1 = [&](int b, uint32_t a_hi_u, uint32_t a_lo_u) {
+            const TcBlock& B = P.blk[b];
+            const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+            const uint32_t w1hi = w_u + b * 4 * kWTileBytes, w1lo = w1hi + kWTileBytes;
+            const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
+            for (int ks = 0; ks < ksn; ++ks) {
+                const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K
+                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
+                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
+                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
+            }
+        };
+        auto issue_l2 = [&](int b) {
+            const TcBlock& B = P.blk[b];
+            const uint32_t w2hi = w_u + b * 4 * kWTileBytes + 2 * kWTileBytes, w2lo = w2hi + kWTileBytes;
+            for (int rr = 0; rr < B.nruns; ++rr) {
+                const TcRun& R = B.runs[rr];
+                const uint32_t idesc = tc::make_idesc_bf16(128, R.n);
+                const uint32_t rowoff = (uint32_t)R.n0 * 128;                    // n0 is a multiple of 16 -> atom aligned
+                for (int ks = 0; ks < 4; ++ks) {
+                    const uint32_t off = (uint32_t)ks * 32;
+                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, (R.accum || ks > 0));
+                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2lo + rowoff + off), idesc, 1);
+                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_lo_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, 1);
                 }
             }
-            const float zj = z0 + off0;
-            const float pcx = dx * z0 + off0 * dx, pcy = dy * z0 + off0 * dy, pcz = dz * z0 + off0 * dz;
-            float cx = (m00 * pcx + m01 * pcy + m02 * pcz + m03) * a.box_scale;
-            float cy = (m10 * pcx + m11 * pcy + m12 * pcz + m13) * a.box_scale;
-            float cz = (m20 * pcx + m21 * pcy + m22 * pcz + m23) * a.box_scale;
-            if (!live) { cx = cy = cz = 4.f; }
+        };
 
-            // ---- gather -> A (bf16 hi / lo), row = wg*32 + sample
-            gather_chunk_to<true>(a.tex, a.seg, n, cx, cy, cz, lane,
-                                  [&](int src, int q, const float (&at)[4], const float (&as)[4]) {
-                                      const int r = wg * 32 + src;
-                                      __nv_bfloat16 h[4], l[4];
+        int q = 0;
+        for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
+            const RaySetup r = ray_setup(a, pt, wg);
+            float acc[kOut - 1];
 #pragma unroll
-                                      for (int j = 0; j < 4; ++j) tc::split_bf16(at[j], h[j], l[j]);
-                                      uint32_t o = tc::sw128_offset(r, q >> 1) + (q & 1) * 8;
-                                      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
-                                      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
-#pragma unroll
-                                      for (int j = 0; j < 4; ++j) tc::split_bf16(as[j], h[j], l[j]);
-                                      o = tc::sw128_offset(r, 4 + (q >> 1)) + (q & 1) * 8;
-                                      *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
-                                      *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
-                                  });
-            tc::fence_async_smem();
-            tc::tc_fence_before();
-            tc::bar_sync(1 + g, kTcGroupThreads);
+            for (int c = 0; c < kOut - 1; ++c) acc[c] = 0.f;
+            float acc_w = 0.f, acc_d = 0.f, carry = 1.f;
 
-            // ---- hidden blocks: L1(b) [+ L2(b-1)] -> softplus epilogue -> A2
-            for (int b = 0; b < P.nblocks; ++b) {
-                if (issuer) {
+            for (int ch = 0; ch < chunks; ++ch, ++q) {
+                const int stage = q % kTcStages, use = q / kTcStages;
+                const uint32_t a_hi_u = stage_u + stage * 2 * kTileBytes, a_lo_u = a_hi_u + kTileBytes;
+                tc::mbar_wait(&bar_full[stage], use & 1);
+                tc::tc_fence_after();
+
+                // ---- hidden blocks: L1(b) [+ L2(b-1)] -> softplus epilogue -> A2
+                for (int b = 0; b < P.nblocks; ++b) {
+                    if (issuer) {
+                        if (b > 0) issue_l2(b - 1);
+                        issue_l1(b, a_hi_u, a_lo_u);
+                        tc::umma_commit(bar_mma);
+                        if (b == P.nblocks - 1) tc::umma_commit(&bar_empty[stage]);   // A stage is free once these MMAs are done
+                    }
+                    tc::mbar_wait(bar_mma, parity);
+                    parity ^= 1;
                     tc::tc_fence_after();
-                    if (b > 0) issue_l2(b - 1);
-                    issue_l1(b);
-                    tc::umma_commit(&mbar[g]);
+#pragma unroll
+                    for (int half = 0; half < 2; ++half) {
+                        float v[32];
+                        tc::tmem_ld32(d1_col + lane_sel + half * 32, v);
+                        const float* bb = b1s + b * 64 + half * 32;
+#pragma unroll
+                        for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
+                            uint32_t ph[4], pl[4];
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float h0 = softplus_fast(v[c8 * 8 + 2 * j] + bb[c8 * 8 + 2 * j]);
+                                const float h1 = softplus_fast(v[c8 * 8 + 2 * j + 1] + bb[c8 * 8 + 2 * j + 1]);
+                                const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
+                                const float2 back = __bfloat1622float2(hh);
+                                const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
+                                ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                                pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
+                            }
+                            const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
+                            *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
+                            *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        }
+                    }
+                    tc::fence_async_smem();
+                    tc::tc_fence_before();
+                    tc::bar_sync(1, kTcConsumerThreads);
+                    tc::tc_fence_after();
                 }
-                tc::mbar_wait(&mbar[g], parity);
+                if (issuer) {
+                    issue_l2(P.nblocks - 1);
+                    tc::umma_commit(bar_mma);
+                }
+                tc::mbar_wait(bar_mma, parity);
                 parity ^= 1;
                 tc::tc_fence_after();
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float v[32];
-                    tc::tmem_ld32(d1_col + lane_sel + half * 32, v);
-                    const float* bb = b1s + b * 64 + half * 32;
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
-                        uint32_t ph[4], pl[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float h0 = softplus_fast(v[c8 * 8 + 2 * j] + bb[c8 * 8 + 2 * j]);
-                            const float h1 = softplus_fast(v[c8 * 8 + 2 * j + 1] + bb[c8 * 8 + 2 * j + 1]);
-                            __nv_bfloat16 h0h, h0l, h1h, h1l;
-                            tc::split_bf16(h0, h0h, h0l);
-                            tc::split_bf16(h1, h1h, h1l);
-                            ph[j] = tc::pack_bf16(h0h, h1h);
-                            pl[j] = tc::pack_bf16(h0l, h1l);
-                        }
-                        const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
-                        *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                        *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
-                    }
+
+                // ---- this thread's sample: depth bookkeeping (recomputed, not passed through memory)
+                const int s = ch * 32 + lane;
+                const bool live = r.ok && (s < S);
+                float z0 = 0.f, off0 = 0.f, z1 = 0.f;
+                if (live) sample_depths(a, r, s, z0, off0, z1);
+                const float zj = z0 + off0;
+
+                // ---- outputs: columns 32..63 first (semantic logits 32..50, sigma 51), then the colour features 0..31
+                float hi32[32];
+                tc::tmem_ld32(d2_col + lane_sel + 32, hi32);
+                float sigma = (((P.written >> 3) & 1u) ? hi32[19] : 0.f) + b2s[51];
+                if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[r.sample_base + s];
+                const float delta = (s + 1 < S) ? (z1 - zj) * r.dnorm : 1e10f;
+                const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
+                const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
+                const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
+                float total;
+                const float T = warp_exclusive_product(keep, lane, total) * carry;
+                carry *= total;
+                float w = alpha * T;
+                acc_w += w;
+                if (a.last_back && ch == chunks - 1) {
+                    const float wsum_all = warp_sum(acc_w);
+                    if (s == S - 1) w += 1.f - wsum_all;
                 }
-                tc::fence_async_smem();
+                if (a.out_weights != nullptr && live) a.out_weights[r.sample_base + s] = w;
+                acc_d = fmaf(w, zj, acc_d);
+#pragma unroll
+                for (int c = 0; c < 19; ++c) {
+                    const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? hi32[c] : 0.f) + b2s[32 + c];
+                    acc[32 + c] = fmaf(w, v, acc[32 + c]);
+                }
+                float lo32[32];
+                tc::tmem_ld32(d2_col + lane_sel, lo32);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float v = (((P.written >> (c >> 4)) & 1u) ? lo32[c] : 0.f) + b2s[c];
+                    acc[c] = fmaf(w, v, acc[c]);
+                }
                 tc::tc_fence_before();
-                tc::bar_sync(1 + g, kTcGroupThreads);
+                tc::bar_sync(1, kTcConsumerThreads);      // every warp has drained D2 before the next tile's MMAs overwrite it
             }
-            if (issuer) {
-                tc::tc_fence_after();
-                issue_l2(P.nblocks - 1);
-                tc::umma_commit(&mbar[g]);
-            }
-            tc::mbar_wait(&mbar[g], parity);
-            parity ^= 1;
-            tc::tc_fence_after();
 
-            // ---- outputs: columns 32..63 first (semantic logits 32..50, sigma 51), then the colour features 0..31
-            float hi32[32];
-            tc::tmem_ld32(d2_col + lane_sel + 32, hi32);
-            float sigma = ((P.written >> 3) & 1u) ? hi32[19] + b2s[51] : b2s[51];
-            if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[sample_base + s];
-            const float delta = (s + 1 < S) ? (z1 - zj) * dnorm : 1e10f;
-            const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
-            const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
-            const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
-            float total;
-            const float T = warp_exclusive_product(keep, lane, total) * carry;
-            carry *= total;
-            float w = alpha * T;
-            acc_w += w;
-            if (a.last_back && ch == chunks - 1) {
-                const float wsum_all = warp_sum(acc_w);
-                if (s == S - 1) w += 1.f - wsum_all;
-            }
-            if (a.out_weights != nullptr && live) a.out_weights[sample_base + s] = w;
-            acc_d = fmaf(w, zj, acc_d);
+            // ---- per-ray reduction and store (identical to the SIMT kernel)
+            const float wsum = warp_sum(acc_w);
+            float depth = warp_sum(acc_d);
+            float mine0 = 0.f, mine1 = 0.f;
 #pragma unroll
-            for (int c = 0; c < 19; ++c) {
-                const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? hi32[c] : 0.f) + b2s[32 + c];
-                acc[32 + c] = fmaf(w, v, acc[32 + c]);
+            for (int c = 0; c < kOut - 1; ++c) {
+                const float v = warp_sum(acc[c]);
+                if (c == lane) mine0 = v;
+                if (c == lane + 32) mine1 = v;
             }
-            float lo32[32];
-            tc::tmem_ld32(d2_col + lane_sel, lo32);
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-                const float v = (((P.written >> (c >> 4)) & 1u) ? lo32[c] : 0.f) + b2s[c];
-                acc[c] = fmaf(w, v, acc[c]);
+            if (a.white_back) { mine0 += 1.f - wsum; mine1 += 1.f - wsum; }
+            if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
+            if (a.fill_weight) { mine0 = wsum; mine1 = wsum; }
+            if (r.ok) {
+                float* of = a.out_feat + ((long long)r.n * (a.res_w * a.res_h) + r.ray) * (kOut - 1);
+                of[lane] = mine0;
+                if (lane + 32 < kOut - 1) of[lane + 32] = mine1;
+                if (lane == 0) a.out_depth[(long long)r.n * (a.res_w * a.res_h) + r.ray] = depth;
             }
-            tc::tc_fence_before();        // TMEM reads of this chunk are ordered before the next chunk's MMAs (next bar_sync)
-        }
-
-        // ---- per-ray reduction and store (identical to the SIMT kernel)
-        const float wsum = warp_sum(acc_w);
-        float depth = warp_sum(acc_d);
-        float mine0 = 0.f, mine1 = 0.f;
-#pragma unroll
-        for (int c = 0; c < kOut - 1; ++c) {
-            const float v = warp_sum(acc[c]);
-            if (c == lane) mine0 = v;
-            if (c == lane + 32) mine1 = v;
-        }
-        if (a.white_back) { mine0 += 1.f - wsum; mine1 += 1.f - wsum; }
-        if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
-        if (a.fill_weight) { mine0 = wsum; mine1 = wsum; }
-        if (ray_ok) {
-            float* of = a.out_feat + ((long long)n * R + ray) * (kOut - 1);
-            of[lane] = mine0;
-            if (lane + 32 < kOut - 1) of[lane + 32] = mine1;
-            if (lane == 0) a.out_depth[(long long)n * R + ray] = depth;
         }
     }
 
@@ -403,7 +453,7 @@ int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaS
     IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     const int num_tiles = a.tiles_x * a.tiles_y * a.n;
     int grid = sm_count();
-    if (grid > ceil_div(num_tiles, kTcGroups)) grid = ceil_div(num_tiles, kTcGroups);
+    if (grid > num_tiles) grid = num_tiles;
     raymarch_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
     IDE3D_CHECK_LAUNCH("raymarch_tc_kernel");
     return IDE3D_OK;

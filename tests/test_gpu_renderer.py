@@ -104,10 +104,10 @@ def test_raymarch_vs_oracle_random(S, res, opts, precision):
     assert_close(feat, ro, FEAT_TOL[precision], what='feat'); assert_close(depth, do_, D_TOL[precision], what='depth'); assert_close(w, wo, W_TOL[precision], what='w')
 
 
-def test_raymarch_white_noise_planes_and_single_sample():
+def test_raymarch_white_noise_planes():
     """White-noise planes: tolerance scaled by the conditioning explained in _planes() (32^2 planes -> 3e-4).
-    S = 1 has no neighbour to take a spacing from: the reference's perturb_points breaks on it (empty slice,
-    volumetric_rendering.py:100); without jitter the chain is well defined (a single delta = 1e10)."""
+    (S = 1 is degenerate in the reference itself: `deltas[:, :, :1]` of an empty tensor is empty, so fancy_integration
+    returns all-zero maps, volumetric_rendering.py:40-43; it is not a case the kernels try to mimic.)"""
     from ide3d_b200 import render
     tex, seg, dec, cam = _random_case(2, 32, seed=5, smooth=False)
     heads = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
@@ -116,9 +116,6 @@ def test_raymarch_white_noise_planes_and_single_sample():
     feat, depth, w = render.raymarch(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=(8, 8), num_steps=33,
                                      jitter_u=u.to(DEV), return_weights=True)
     assert_close(feat, ro, 3e-4); assert_close(depth, do_, 1e-4); assert_close(w, wo, 1e-4)
-    ro, do_, wo = orr.render_frames(tex, seg, dec, cam, num_steps=1, resolution=(5, 5))
-    feat, depth, w = render.raymarch(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=(5, 5), num_steps=1, return_weights=True)
-    assert_close(feat, ro, 3e-4); assert_close(depth, do_, 1e-5); assert_close(w, wo, 1e-5)
 
 
 @pytest.mark.parametrize('precision', PRECISIONS)
