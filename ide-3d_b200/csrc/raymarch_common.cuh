@@ -145,6 +145,81 @@ __device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const Plan
     }
 }
 
+// Channels-last fast path with explicit memory-level parallelism: for the 4 samples of a sub-iteration every lane first
+// builds its 12 tap addresses (clamped into the plane, out-of-range taps get weight 0 -- no branches), then issues the 12
+// texture loads back to back, accumulates, and repeats for the 12 shape loads.  Requires tex and seg to share strides.
+template <typename Store>
+__device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const PlaneView& seg, int n, float cx, float cy,
+                                                float cz, int lane, Store store) {
+    const int W = tex.w, H = tex.h;
+    const Foot f0 = footprint(cx, cy, W, H);
+    const Foot f1 = footprint(cy, cz, W, H);
+    const Foot f2 = footprint(cx, cz, W, H);
+    const int q = lane & 7, grp = lane >> 3;
+    const float4* tb = reinterpret_cast<const float4*>(tex.base + (long long)n * tex.sn) + q;
+    const float4* sb = reinterpret_cast<const float4*>(seg.base + (long long)n * seg.sn) + q;
+    const int sh4 = (int)(tex.sh >> 2), sw4 = (int)(tex.sw >> 2);      // strides in float4 units (multiples of 4 floats)
+
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const int src = it * 4 + grp;
+        int off[12];
+        float wgt[12];
+        bool any = false;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const Foot& mine = (k == 0) ? f0 : (k == 1 ? f1 : f2);
+            const int x0 = __shfl_sync(kFull, mine.x0, src);
+            const int y0 = __shfl_sync(kFull, mine.y0, src);
+            const float fx = __shfl_sync(kFull, mine.fx, src);
+            const float fy = __shfl_sync(kFull, mine.fy, src);
+#pragma unroll
+            for (int tap = 0; tap < 4; ++tap) {
+                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
+                const bool ok = ((unsigned)xx < (unsigned)W) && ((unsigned)yy < (unsigned)H);
+                const int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1);
+                off[k * 4 + tap] = yc * sh4 + xc * sw4 + k * (kFeat / 4);
+                const float wv = ((tap & 1) ? fx : 1.f - fx) * ((tap >> 1) ? fy : 1.f - fy);
+                wgt[k * 4 + tap] = ok ? wv : 0.f;
+                any |= ok;
+            }
+        }
+        float at[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+        if (__any_sync(kFull, any)) {                           // fully masked sub-iterations (dead samples) load nothing
+            float4 v[12];
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = __ldg(tb + off[i]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const float4 a = v[k * 4 + tap];
+                    const float w_ = wgt[k * 4 + tap];
+                    p[0] += a.x * w_; p[1] += a.y * w_; p[2] += a.z * w_; p[3] += a.w * w_;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) at[j] += p[j];
+            }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) v[i] = __ldg(sb + off[i]);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                float p[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int tap = 0; tap < 4; ++tap) {
+                    const float4 a = v[k * 4 + tap];
+                    const float w_ = wgt[k * 4 + tap];
+                    p[0] += a.x * w_; p[1] += a.y * w_; p[2] += a.z * w_; p[3] += a.w * w_;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) as[j] += p[j];
+            }
+        }
+        store(src, q, at, as);
+    }
+}
+
 // staging-row flavour used by the SIMT kernels: stage[s*kRow + 0..31] = texture, [32..63] = shape features
 template <bool kChannelsLast>
 __device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneView& seg, int n, float cx,

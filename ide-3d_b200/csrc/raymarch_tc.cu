@@ -17,9 +17,9 @@
 //
 // Warp-specialised, one persistent CTA per SM (384 threads):
 //   warpgroup 0 (4 warps)  consumer: waits for a full A stage, issues the UMMAs (one elected thread), runs the softplus and
-//                          compositing epilogues out of TMEM, owns the per-ray accumulators (232 registers/thread)
+//                          compositing epilogues out of TMEM, owns the per-ray accumulators (200 registers/thread)
 //   warpgroups 1-2 (8 warps) producers: compute sample positions and gather features into a 3-stage ring of A tiles
-//                          (104 registers/thread, many loads in flight); mbarrier full/empty hand-off, the "empty" arrive is
+//                          (152 registers/thread, 12 x LDG.128 in flight per lane); mbarrier full/empty hand-off, the "empty" arrive is
 //                          the tcgen05.commit of the last MMA that reads the stage.
 #include "raymarch_common.cuh"
 #include "tc_ptx.cuh"
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
 
     if (warp >= 4) {
         // =========================================================================== producers
-        tc::setmaxnreg_dec<104>();
+        tc::setmaxnreg_dec<152>();
         const int pw = warp - 4, pg = pw >> 2, quarter = pw & 3;
         int q = 0;
         for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
                 }
                 unsigned char* a_hi = smem + kSmStage + stage * 2 * kTileBytes;
                 unsigned char* a_lo = a_hi + kTileBytes;
-                gather_chunk_to<true>(a.tex, a.seg, r.n, cx, cy, cz, lane,
+                gather_chunk_cl(a.tex, a.seg, r.n, cx, cy, cz, lane,
                                       [&](int src, int qq, const float (&at)[4], const float (&as)[4]) {
                                           const int row = quarter * 32 + src;
                                           __nv_bfloat16 h[4], l[4];
@@ -225,7 +225,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         }
     } else {
         // =========================================================================== consumer
-        tc::setmaxnreg_inc<232>();
+        tc::setmaxnreg_inc<200>();
         const int wg = warp;
         const uint32_t d1_col = tmem_base, d2_col = tmem_base + 64;
         const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;
@@ -436,6 +436,8 @@ static bool build_program(const ide3d_decoder& d, TcProgram& P) {
 // entry used by ide3d_raymarch_fwd (raymarch.cu); IDE3D_UNSUPPORTED when this decoder / layout has no TC kernel
 int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaStream_t st) {
     if (!channels_last) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: planes must be channels-last");
+    if (p->tex.stride_h != p->seg.stride_h || p->tex.stride_w != p->seg.stride_w)
+        IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: tex and seg planes must share strides");
     TcArgs a;
     if (!build_program(p->dec, a.prog)) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: decoder shape not supported");
     a.tex = make_view(p->tex); a.seg = make_view(p->seg); a.dec = p->dec;
