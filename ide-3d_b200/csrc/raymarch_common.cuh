@@ -57,6 +57,13 @@ __device__ __forceinline__ float jitter_hash(uint32_t idx, uint32_t lo, uint32_t
 __device__ __forceinline__ float softplus_fast(float x) {
     return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
 }
+// same function on bare MUFU instructions (ftz forms: no denormal pre/post-scaling code around ex2 / lg2): 7 instructions
+__device__ __forceinline__ float softplus_mufu(float x) {
+    float t, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * -1.4426950408889634f));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + t));
+    return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
+}
 // density activation: full precision, matters because delta_last = 1e10 amplifies tiny values
 __device__ __forceinline__ float softplus_precise(float x) {
     return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
@@ -148,7 +155,7 @@ __device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const Plan
 // Channels-last fast path with explicit memory-level parallelism: for the 4 samples of a sub-iteration every lane first
 // builds its 12 tap addresses (clamped into the plane, out-of-range taps get weight 0 -- no branches), then issues the 12
 // texture loads back to back, accumulates, and repeats for the 12 shape loads.  Requires tex and seg to share strides.
-template <typename Store>
+template <bool kAllInFlight = false, typename Store>
 __device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const PlaneView& seg, int n, float cx, float cy,
                                                 float cz, int lane, Store store) {
     const int W = tex.w, H = tex.h;
@@ -187,8 +194,13 @@ __device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const Plan
         float at[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
         if (__any_sync(kFull, any)) {                           // fully masked sub-iterations (dead samples) load nothing
             float4 v[12];
+            float4 u[kAllInFlight ? 12 : 1];
 #pragma unroll
             for (int i = 0; i < 12; ++i) v[i] = __ldg(tb + off[i]);
+            if (kAllInFlight) {
+#pragma unroll
+                for (int i = 0; i < 12; ++i) u[kAllInFlight ? i : 0] = __ldg(sb + off[i]);     // all 24 LDG.128 in flight
+            }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float p[4] = {0.f, 0.f, 0.f, 0.f};
@@ -202,7 +214,7 @@ __device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const Plan
                 for (int j = 0; j < 4; ++j) at[j] += p[j];
             }
 #pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = __ldg(sb + off[i]);
+            for (int i = 0; i < 12; ++i) v[i] = kAllInFlight ? u[kAllInFlight ? i : 0] : __ldg(sb + off[i]);
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 float p[4] = {0.f, 0.f, 0.f, 0.f};

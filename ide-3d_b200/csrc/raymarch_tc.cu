@@ -15,32 +15,37 @@
 // operands carry 16 mantissa bits, the dropped lo*lo term is 2^-16 relative.  Measured against the fp32 oracle in
 // tests/test_gpu_renderer.py (tolerance stated there).
 //
-// Warp-specialised, one persistent CTA per SM (384 threads):
-//   warpgroup 0 (4 warps)  consumer: waits for a full A stage, issues the UMMAs (one elected thread), runs the softplus and
-//                          compositing epilogues out of TMEM, owns the per-ray accumulators (200 registers/thread)
-//   warpgroups 1-2 (8 warps) producers: compute sample positions and gather features into a 3-stage ring of A tiles
-//                          (152 registers/thread, 12 x LDG.128 in flight per lane); mbarrier full/empty hand-off, the "empty" arrive is
-//                          the tcgen05.commit of the last MMA that reads the stage.
+// Warp-specialised, one persistent CTA per SM (512 threads):
+//   warpgroups 0-1 (8 warps) consumers: wait for a full A stage, issue the UMMAs (one elected thread), run the softplus and
+//                          compositing epilogues out of TMEM.  Warp w and w+4 share TMEM lanes 32*(w%4).. and split the
+//                          columns: in the softplus epilogue each takes 32 of the 64 hidden units; in the final epilogue the
+//                          lower warp takes sigma + the 19 semantic logits (and computes the compositing weight), the upper
+//                          warp the 32 colour features (weight handed over through shared memory).  104 registers/thread.
+//   warpgroups 2-3 (8 warps) producers: compute sample positions and gather features into a 3-stage ring of A tiles
+//                          (152 registers/thread, 24 x LDG.128 in flight per lane); mbarrier full/empty hand-off, the "empty"
+//                          arrive is the tcgen05.commit of the last MMA that reads the stage.
+#include <stdlib.h>
+
 #include "raymarch_common.cuh"
 #include "tc_ptx.cuh"
 
 namespace ide3d {
 
-constexpr int kTcConsumerThreads = 128;
+constexpr int kTcConsumerThreads = 256;                       // 8 warps: (TMEM lane quarter) x (column half)
 constexpr int kTcProducerWarps = 8;
 constexpr int kTcThreads = kTcConsumerThreads + kTcProducerWarps * 32;
 constexpr int kTcStages = 3;
 constexpr int kTcMaxBlocks = 3;
 constexpr int kTileBytes = 128 * 128;                         // [128 rows x 64 bf16]
 constexpr int kWTileBytes = 64 * 128;                         // [64 rows x 64 bf16]
-constexpr int kTmemCols = 128;                                // D1 64 + D2 64
+constexpr int kTmemCols = 256;                                // D1 3 x 64 (one per hidden block) + D2 64
 
 // ---- shared memory map (bytes) ----
 constexpr int kSmW = 0;                                       // per block: W1 hi, W1 lo, W2 hi, W2 lo (8 KB each)
 constexpr int kSmA2 = kSmW + kTcMaxBlocks * 4 * kWTileBytes;                // 98304: A2 hi, A2 lo
 constexpr int kSmStage = kSmA2 + 2 * kTileBytes;                             // 131072: kTcStages x (A hi, A lo)
 constexpr int kSmMisc = kSmStage + kTcStages * 2 * kTileBytes;              // 229376
-constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64) * 4 + 128;            // b1[192], b2[64], mbarriers, tmem ptr
+constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64 + 128 + 8) * 4 + 128;  // b1[192], b2[64], w hand-off[128], wsum[4+4], mbarriers, tmem ptr
 constexpr int kTcSmemBytes = kSmMisc + kSmMiscBytes + 1024;                 // + slack for the 1024-byte alignment
 
 struct TcRun { int n0, n, accum; };
@@ -72,6 +77,7 @@ struct TcArgs {
     const float* noise;
     float *out_feat, *out_depth, *out_weights;
     int tiles_x, tiles_y;
+    int debug;                                     // IDE3D_TC_DEBUG: 1 = producers skip the gather, 2 = consumer skips the decoder (timing experiments only)
 };
 
 // write element (row, k) of a [rows x 64] bf16 swizzle-128B tile
@@ -131,7 +137,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     float* b1s = reinterpret_cast<float*>(smem + kSmMisc);
     float* b2s = b1s + kTcMaxBlocks * 64;
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b2s + 64);        // [kTcStages] producers -> consumer
+    float* wbuf = b2s + 64;                                              // [128] compositing weight of each row (half 0 -> half 1)
+    float* wsumbuf = wbuf + 128;                                         // [4] weights_sum of the 4 rays
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(wsumbuf + 8);      // [kTcStages] producers -> consumer
     uint64_t* bar_empty = bar_full + kTcStages;                        // [kTcStages] consumer (tcgen05.commit) -> producers
     uint64_t* bar_mma = bar_empty + kTcStages;                         // consumer-internal: MMA batch done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
@@ -179,10 +187,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
     const int num_ptiles = a.tiles_x * a.tiles_y * a.n;
     const int chunks = (S + 31) >> 5;
 
-    if (warp >= 4) {
+    if (warp >= 8) {
         // =========================================================================== producers
-        tc::setmaxnreg_dec<152>();
-        const int pw = warp - 4, pg = pw >> 2, quarter = pw & 3;
+        tc::setmaxnreg_inc<152>();
+        const int pw = warp - 8, pg = pw >> 2, quarter = pw & 3;
         int q = 0;
         for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
             const RaySetup r = ray_setup(a, pt, quarter);
@@ -203,7 +211,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
                 }
                 unsigned char* a_hi = smem + kSmStage + stage * 2 * kTileBytes;
                 unsigned char* a_lo = a_hi + kTileBytes;
-                gather_chunk_cl(a.tex, a.seg, r.n, cx, cy, cz, lane,
+                if (a.debug != 1) gather_chunk_cl<true>(a.tex, a.seg, r.n, cx, cy, cz, lane,
                                       [&](int src, int qq, const float (&at)[4], const float (&as)[4]) {
                                           const int row = quarter * 32 + src;
                                           __nv_bfloat16 h[4], l[4];
@@ -224,17 +232,17 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
             }
         }
     } else {
-        // =========================================================================== consumer
-        tc::setmaxnreg_inc<200>();
-        const int wg = warp;
-        const uint32_t d1_col = tmem_base, d2_col = tmem_base + 64;
+        // =========================================================================== consumers
+        tc::setmaxnreg_dec<104>();
+        const int wg = warp & 3, half = warp >> 2;                 // TMEM lane quarter (= ray of the 2x2 tile), column half
+        const uint32_t d1_col = tmem_base, d2_col = tmem_base + 64 * kTcMaxBlocks;
         const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;
         unsigned char* a2_hi = smem + kSmA2;
         unsigned char* a2_lo = a2_hi + kTileBytes;
         const uint32_t a2_hi_u = tc::smem_u32(a2_hi), a2_lo_u = tc::smem_u32(a2_lo);
         const uint32_t w_u = tc::smem_u32(smem + kSmW);
         const uint32_t stage_u = tc::smem_u32(smem + kSmStage);
-        const bool issuer = (wg == 0 && lane == 0);
+        const bool issuer = (warp == 0 && lane == 0);
         const int row = wg * 32 + lane;
         uint32_t parity = 0;
 
@@ -245,9 +253,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
             const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
             for (int ks = 0; ks < ksn; ++ks) {
                 const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K
-                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
-                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
-                tc::umma_bf16(d1_col, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
+                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
+                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
+                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
             }
         };
         auto issue_l2 = [&](int b) {
@@ -269,9 +277,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         int q = 0;
         for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
             const RaySetup r = ray_setup(a, pt, wg);
-            float acc[kOut - 1];
+            // half 0: semantic logits (19) ; half 1: colour features (32).  acc[32] covers both.
+            float acc[32];
 #pragma unroll
-            for (int c = 0; c < kOut - 1; ++c) acc[c] = 0.f;
+            for (int c = 0; c < 32; ++c) acc[c] = 0.f;
             float acc_w = 0.f, acc_d = 0.f, carry = 1.f;
 
             for (int ch = 0; ch < chunks; ++ch, ++q) {
@@ -279,116 +288,146 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
                 const uint32_t a_hi_u = stage_u + stage * 2 * kTileBytes, a_lo_u = a_hi_u + kTileBytes;
                 tc::mbar_wait(&bar_full[stage], use & 1);
                 tc::tc_fence_after();
+                if (a.debug == 2) {                                      // timing experiment: hand the stage straight back
+                    tc::bar_sync(1, kTcConsumerThreads);
+                    if (issuer) tc::mbar_arrive(&bar_empty[stage]);
+                    continue;
+                }
 
-                // ---- hidden blocks: L1(b) [+ L2(b-1)] -> softplus epilogue -> A2
+                // ---- layer 1 of every hidden block in one batch (D1 has a 64-column slot per block); the A stage is free after it
+                if (issuer) {
+                    for (int b = 0; b < P.nblocks; ++b) issue_l1(b, a_hi_u, a_lo_u);
+                    tc::umma_commit(bar_mma);
+                    tc::umma_commit(&bar_empty[stage]);
+                }
+                tc::mbar_wait(bar_mma, parity);
+                parity ^= 1;
+                tc::tc_fence_after();
+                // ---- per block: softplus epilogue in registers -> (wait until layer 2 of the previous block has read A2) -> A2
+                //      -> layer 2 of this block is issued and runs while the next block's softplus is being computed
                 for (int b = 0; b < P.nblocks; ++b) {
-                    if (issuer) {
-                        if (b > 0) issue_l2(b - 1);
-                        issue_l1(b, a_hi_u, a_lo_u);
-                        tc::umma_commit(bar_mma);
-                        if (b == P.nblocks - 1) tc::umma_commit(&bar_empty[stage]);   // A stage is free once these MMAs are done
-                    }
-                    tc::mbar_wait(bar_mma, parity);
-                    parity ^= 1;
-                    tc::tc_fence_after();
-#pragma unroll
-                    for (int half = 0; half < 2; ++half) {
+                    uint32_t ph[16], pl[16];
+                    {
                         float v[32];
-                        tc::tmem_ld32(d1_col + lane_sel + half * 32, v);
+                        tc::tmem_ld32(d1_col + b * 64 + lane_sel + half * 32, v);
                         const float* bb = b1s + b * 64 + half * 32;
 #pragma unroll
-                        for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
-                            uint32_t ph[4], pl[4];
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float h0 = softplus_fast(v[c8 * 8 + 2 * j] + bb[c8 * 8 + 2 * j]);
-                                const float h1 = softplus_fast(v[c8 * 8 + 2 * j + 1] + bb[c8 * 8 + 2 * j + 1]);
-                                const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
-                                const float2 back = __bfloat1622float2(hh);
-                                const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
-                                ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
-                                pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
-                            }
-                            const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
-                            *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[0], ph[1], ph[2], ph[3]);
-                            *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                        for (int j = 0; j < 16; ++j) {
+                            const float h0 = softplus_mufu(v[2 * j] + bb[2 * j]);
+                            const float h1 = softplus_mufu(v[2 * j + 1] + bb[2 * j + 1]);
+                            const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
+                            const float2 back = __bfloat1622float2(hh);
+                            const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
+                            ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
+                            pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
                         }
+                    }
+                    if (b > 0) {                                             // A2 is still being read by layer 2 of block b-1
+                        tc::mbar_wait(bar_mma, parity);
+                        parity ^= 1;
+                    }
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
+                        const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
+                        *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[c8 * 4], ph[c8 * 4 + 1], ph[c8 * 4 + 2], ph[c8 * 4 + 3]);
+                        *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[c8 * 4], pl[c8 * 4 + 1], pl[c8 * 4 + 2], pl[c8 * 4 + 3]);
                     }
                     tc::fence_async_smem();
                     tc::tc_fence_before();
                     tc::bar_sync(1, kTcConsumerThreads);
                     tc::tc_fence_after();
-                }
-                if (issuer) {
-                    issue_l2(P.nblocks - 1);
-                    tc::umma_commit(bar_mma);
+                    if (issuer) {
+                        issue_l2(b);
+                        tc::umma_commit(bar_mma);
+                    }
                 }
                 tc::mbar_wait(bar_mma, parity);
                 parity ^= 1;
                 tc::tc_fence_after();
 
-                // ---- this thread's sample: depth bookkeeping (recomputed, not passed through memory)
                 const int s = ch * 32 + lane;
                 const bool live = r.ok && (s < S);
-                float z0 = 0.f, off0 = 0.f, z1 = 0.f;
-                if (live) sample_depths(a, r, s, z0, off0, z1);
-                const float zj = z0 + off0;
-
-                // ---- outputs: columns 32..63 first (semantic logits 32..50, sigma 51), then the colour features 0..31
-                float hi32[32];
-                tc::tmem_ld32(d2_col + lane_sel + 32, hi32);
-                float sigma = (((P.written >> 3) & 1u) ? hi32[19] : 0.f) + b2s[51];
-                if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[r.sample_base + s];
-                const float delta = (s + 1 < S) ? (z1 - zj) * r.dnorm : 1e10f;
-                const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
-                const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
-                const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
-                float total;
-                const float T = warp_exclusive_product(keep, lane, total) * carry;
-                carry *= total;
-                float w = alpha * T;
-                acc_w += w;
-                if (a.last_back && ch == chunks - 1) {
-                    const float wsum_all = warp_sum(acc_w);
-                    if (s == S - 1) w += 1.f - wsum_all;
-                }
-                if (a.out_weights != nullptr && live) a.out_weights[r.sample_base + s] = w;
-                acc_d = fmaf(w, zj, acc_d);
+                float o32[32];
+                if (half == 0) {
+                    // ---- sigma + semantic logits (columns 32..63), compositing weight of this sample
+                    float z0 = 0.f, off0 = 0.f, z1 = 0.f;
+                    if (live) sample_depths(a, r, s, z0, off0, z1);
+                    const float zj = z0 + off0;
+                    tc::tmem_ld32(d2_col + lane_sel + 32, o32);
+                    float sigma = (((P.written >> 3) & 1u) ? o32[19] : 0.f) + b2s[51];
+                    if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[r.sample_base + s];
+                    const float delta = (s + 1 < S) ? (z1 - zj) * r.dnorm : 1e10f;
+                    const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
+                    const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
+                    const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
+                    float total;
+                    const float T = warp_exclusive_product(keep, lane, total) * carry;
+                    carry *= total;
+                    float w = alpha * T;
+                    acc_w += w;
+                    if (a.last_back && ch == chunks - 1) {
+                        const float wsum_all = warp_sum(acc_w);
+                        if (s == S - 1) w += 1.f - wsum_all;
+                    }
+                    wbuf[row] = w;                                           // hand the weight to the colour warp
+                    tc::bar_sync(2 + wg, 64);
+                    if (a.out_weights != nullptr && live) a.out_weights[r.sample_base + s] = w;
+                    acc_d = fmaf(w, zj, acc_d);
 #pragma unroll
-                for (int c = 0; c < 19; ++c) {
-                    const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? hi32[c] : 0.f) + b2s[32 + c];
-                    acc[32 + c] = fmaf(w, v, acc[32 + c]);
-                }
-                float lo32[32];
-                tc::tmem_ld32(d2_col + lane_sel, lo32);
+                    for (int c = 0; c < 19; ++c) {
+                        const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? o32[c] : 0.f) + b2s[32 + c];
+                        acc[c] = fmaf(w, v, acc[c]);
+                    }
+                } else {
+                    // ---- colour features (columns 0..31)
+                    tc::tmem_ld32(d2_col + lane_sel, o32);
+                    tc::bar_sync(2 + wg, 64);
+                    const float w = wbuf[row];
 #pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float v = (((P.written >> (c >> 4)) & 1u) ? lo32[c] : 0.f) + b2s[c];
-                    acc[c] = fmaf(w, v, acc[c]);
+                    for (int c = 0; c < 32; ++c) {
+                        const float v = (((P.written >> (c >> 4)) & 1u) ? o32[c] : 0.f) + b2s[c];
+                        acc[c] = fmaf(w, v, acc[c]);
+                    }
                 }
                 tc::tc_fence_before();
-                tc::bar_sync(1, kTcConsumerThreads);      // every warp has drained D2 before the next tile's MMAs overwrite it
+                tc::bar_sync(1, kTcConsumerThreads);      // D2 drained and wbuf consumed before the next tile reuses them
             }
 
-            // ---- per-ray reduction and store (identical to the SIMT kernel)
-            const float wsum = warp_sum(acc_w);
-            float depth = warp_sum(acc_d);
-            float mine0 = 0.f, mine1 = 0.f;
+            // ---- per-ray reduction and store
+            const long long ray_index = (long long)r.n * (a.res_w * a.res_h) + r.ray;
+            float* of = a.out_feat + ray_index * (kOut - 1);
+            if (half == 0) {
+                const float wsum = warp_sum(acc_w);
+                if (lane == 0) wsumbuf[wg] = wsum;
+                tc::bar_sync(2 + wg, 64);
+                float depth = warp_sum(acc_d);
+                float mine = 0.f;
 #pragma unroll
-            for (int c = 0; c < kOut - 1; ++c) {
-                const float v = warp_sum(acc[c]);
-                if (c == lane) mine0 = v;
-                if (c == lane + 32) mine1 = v;
+                for (int c = 0; c < 19; ++c) {
+                    const float v = warp_sum(acc[c]);
+                    if (c == lane) mine = v;
+                }
+                if (a.white_back) mine += 1.f - wsum;
+                if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
+                if (a.fill_weight) mine = wsum;
+                if (r.ok) {
+                    if (lane < 19) of[32 + lane] = mine;
+                    if (lane == 0) a.out_depth[ray_index] = depth;
+                }
+            } else {
+                tc::bar_sync(2 + wg, 64);
+                const float wsum = wsumbuf[wg];
+                float mine = 0.f;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) {
+                    const float v = warp_sum(acc[c]);
+                    if (c == lane) mine = v;
+                }
+                if (a.white_back) mine += 1.f - wsum;
+                if (a.fill_weight) mine = wsum;
+                if (r.ok) of[lane] = mine;
             }
-            if (a.white_back) { mine0 += 1.f - wsum; mine1 += 1.f - wsum; }
-            if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
-            if (a.fill_weight) { mine0 = wsum; mine1 = wsum; }
-            if (r.ok) {
-                float* of = a.out_feat + ((long long)r.n * (a.res_w * a.res_h) + r.ray) * (kOut - 1);
-                of[lane] = mine0;
-                if (lane + 32 < kOut - 1) of[lane + 32] = mine1;
-                if (lane == 0) a.out_depth[(long long)r.n * (a.res_w * a.res_h) + r.ray] = depth;
-            }
+            tc::bar_sync(1, kTcConsumerThreads);          // wsumbuf is reused by the next pixel tile
         }
     }
 
@@ -452,6 +491,8 @@ int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaS
     a.noise_std = p->noise_std; a.noise = (p->noise_std != 0.f) ? p->noise : nullptr;
     a.out_feat = p->out_feat; a.out_depth = p->out_depth; a.out_weights = p->out_weights;
     a.tiles_x = ceil_div(p->res_w, 2); a.tiles_y = ceil_div(p->res_h, 2);
+    const char* dbg = getenv("IDE3D_TC_DEBUG");
+    a.debug = dbg ? atoi(dbg) : 0;
     IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     const int num_tiles = a.tiles_x * a.tiles_y * a.n;
     int grid = sm_count();
