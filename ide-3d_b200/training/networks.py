@@ -9,11 +9,16 @@ Every convolution goes to cuDNN (conv2d_resample -> conv2d_gradfix); the surroun
 sm_100a kernels: upfirdn2d (FIR after the transposed conv, skip-image upsampling) and bias_act.
 """
 
+import os
+
 import numpy as np
 import torch
 
 from ..torch_utils import misc, persistence
 from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
+
+
+FUSED_MODCONV_MIN_RES = 1 << 30      # block resolutions >= this use the grouped (weight-modulated) convolution
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -29,12 +34,15 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
         weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
         styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
     w = dcoefs = None
-    if demodulate or fused_modconv:
+    if fused_modconv:
         w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)            # [N,O,I,k,k]
-    if demodulate:
-        dcoefs = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()                       # [N,O]
     if demodulate and fused_modconv:
+        dcoefs = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()                       # [N,O]
         w = w * dcoefs.reshape(batch_size, -1, 1, 1, 1)
+    elif demodulate:
+        # sum_{i,k} (W[o,i,k] s[n,i])^2 = sum_i s[n,i]^2 sum_k W[o,i,k]^2 : a [N,I] x [I,O] product instead of
+        # materialising the [N,O,I,k,k] modulated weight just to reduce it (same value up to fp32 summation order)
+        dcoefs = (styles.square() @ weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
 
     if not fused_modconv:                           # scale activations instead of weights (:97-111)
         x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
@@ -228,6 +236,11 @@ class SynthesisBlock(torch.nn.Module):
         memory_format = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
         if fused_modconv is None:
             fused_modconv = (not self.training) and (dtype == torch.float32 or int(ws.shape[0]) == 1)
+            # Scaling activations instead of weights keeps the convolution a plain batched one (the grouped per-sample
+            # form is what the reference uses in eval, inversion/networks.py:802; both are the same arithmetic up to
+            # rounding) and is faster below FUSED_MODCONV_MIN_RES on B200 (measured).
+            thr = int(os.environ.get('IDE3D_FUSED_MODCONV_MIN_RES', FUSED_MODCONV_MIN_RES))
+            fused_modconv = fused_modconv and self.resolution >= thr
         if self.in_channels == 0:
             x = self.const.to(dtype=dtype, memory_format=memory_format)
             x = x.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
