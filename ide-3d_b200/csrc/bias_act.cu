@@ -96,14 +96,49 @@ template <> __device__ __forceinline__ float to_acc<__half>(__half v) { return _
 template <typename T> __device__ __forceinline__ T from_acc(typename Acc<T>::type v) { return (T)v; }
 template <> __device__ __forceinline__ __half from_acc<__half>(float v) { return __float2half(v); }
 
+// one 16-byte vector <-> N accumulator-typed registers (explicit unpacking: no local-memory round trip)
+__device__ __forceinline__ void load_vec(const float* p, long long v, float (&o)[4]) {
+    const float4 t = __ldcs(reinterpret_cast<const float4*>(p) + v);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+__device__ __forceinline__ void load_vec(const double* p, long long v, double (&o)[2]) {
+    const double2 t = __ldcs(reinterpret_cast<const double2*>(p) + v);
+    o[0] = t.x; o[1] = t.y;
+}
+__device__ __forceinline__ void load_vec(const __half* p, long long v, float (&o)[8]) {
+    const uint4 t = __ldcs(reinterpret_cast<const uint4*>(p) + v);
+    const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void store_vec(float* p, long long v, const float (&o)[4]) {
+    __stcs(reinterpret_cast<float4*>(p) + v, make_float4(o[0], o[1], o[2], o[3]));
+}
+__device__ __forceinline__ void store_vec(double* p, long long v, const double (&o)[2]) {
+    __stcs(reinterpret_cast<double2*>(p) + v, make_double2(o[0], o[1]));
+}
+__device__ __forceinline__ void store_vec(__half* p, long long v, const float (&o)[8]) {
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 h = __floats2half2_rn(o[2 * i], o[2 * i + 1]);
+        w[i] = *reinterpret_cast<const unsigned*>(&h);
+    }
+    __stcs(reinterpret_cast<uint4*>(p) + v, make_uint4(w[0], w[1], w[2], w[3]));
+}
+
 // Vectorised kernel: every thread handles whole 16-byte vectors; the tail (size_x % N) is scalar.
-template <typename T, int A, int UNROLL>
-__global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
+// Bias addressing per vector: BMODE 0 = none, 1 = one bias for the whole vector (step_b % N == 0: NCHW),
+// 2 = consecutive biases (step_b == 1 and size_b % N == 0: channels_last / [M, C] matrices), 3 = per element.
+template <typename T, int A, int UNROLL, bool kFwd>
+__global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p, const int bmode) {
     using S = typename Acc<T>::type;
-    using V = typename Vec<T>::type;
     constexpr int N = Vec<T>::N;
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
-    const int G = p.grad;
+    const int G = kFwd ? 0 : p.grad;          // forward-only instantiation: the gradient forms fold away
     const T* x = (const T*)p.x;
     const T* b = (const T*)p.b;
     const T* xref = (const T*)p.xref;
@@ -112,37 +147,40 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
     T* y = (T*)p.y;
     const long long nvec = p.size_x / N;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    const bool b_uniform = (b != nullptr) && (p.step_b % N == 0);   // one bias per vector
     const bool small = p.size_x <= 0x7fffffffll;
 
     for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
-        V vx[UNROLL];
+        S vx[UNROLL][N];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long v = v0 + u * stride;
-            if (v < nvec) vx[u] = __ldcs(reinterpret_cast<const V*>(x) + v);      // streaming: read once
+            if (v < nvec) load_vec(x, v, vx[u]);                              // all loads of the unrolled group first
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const long long v = v0 + u * stride;
             if (v >= nvec) continue;
             const long long e0 = v * N;
-            alignas(16) T ex[N]; alignas(16) T exr[N]; alignas(16) T eyr[N]; alignas(16) T edy[N]; alignas(16) T out[N];
-            *reinterpret_cast<V*>(ex) = vx[u];
-            if (xref) *reinterpret_cast<V*>(exr) = __ldcs(reinterpret_cast<const V*>(xref) + v);
-            if (yref) *reinterpret_cast<V*>(eyr) = __ldcs(reinterpret_cast<const V*>(yref) + v);
-            if (dy) *reinterpret_cast<V*>(edy) = __ldcs(reinterpret_cast<const V*>(dy) + v);
-            S bu = 0;
-            if (b_uniform) bu = to_acc<T>(b[bias_index(e0, p, small)]);
+            S exr[N], eyr[N], edy[N], out[N], bb[N];
+            if (xref) load_vec(xref, v, exr);
+            if (yref) load_vec(yref, v, eyr);
+            if (dy) load_vec(dy, v, edy);
+            if (bmode == 1) {
+                const S t = to_acc<T>(b[bias_index(e0, p, small)]);
 #pragma unroll
-            for (int j = 0; j < N; ++j) {
-                S bb = bu;
-                if (b != nullptr && !b_uniform) bb = to_acc<T>(b[bias_index(e0 + j, p, small)]);
-                out[j] = from_acc<T>(eval<S, A>(to_acc<T>(ex[j]), bb, xref ? to_acc<T>(exr[j]) : (S)0,
-                                                yref ? to_acc<T>(eyr[j]) : (S)0, dy ? to_acc<T>(edy[j]) : (S)1, G,
-                                                alpha, gain, clamp));
+                for (int j = 0; j < N; ++j) bb[j] = t;
+            } else if (bmode == 2) {
+                const long long i0 = small ? (long long)((unsigned)e0 % (unsigned)p.size_b) : e0 % p.size_b;
+#pragma unroll
+                for (int j = 0; j < N; ++j) bb[j] = to_acc<T>(b[i0 + j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < N; ++j) bb[j] = (bmode == 3) ? to_acc<T>(b[bias_index(e0 + j, p, small)]) : (S)0;
             }
-            __stcs(reinterpret_cast<V*>(y) + v, *reinterpret_cast<V*>(out));
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                out[j] = eval<S, A>(vx[u][j], bb[j], xref ? exr[j] : (S)0, yref ? eyr[j] : (S)0, dy ? edy[j] : (S)1, G, alpha, gain, clamp);
+            store_vec(y, v, out);
         }
     }
     // scalar tail
@@ -155,6 +193,44 @@ __global__ void __launch_bounds__(256) bias_act_kernel(const BiasActArgs p) {
     }
 }
 
+// Planar fast path (no bias, or NCHW-style bias with step_b >= 1024 elements): the work is cut into
+// (plane, chunk) items so that the bias is BLOCK-uniform -- no per-thread index arithmetic beyond an add.
+template <typename T, int A, int UNROLL, bool kFwd>
+__global__ void __launch_bounds__(256) bias_act_planar_kernel(const BiasActArgs p, long long plane_elems, long long chunks_per_plane,
+                                                             long long items) {
+    using S = typename Acc<T>::type;
+    constexpr int N = Vec<T>::N;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const int G = kFwd ? 0 : p.grad;          // forward-only instantiation: the gradient forms fold away
+    const T* b = (const T*)p.b;
+    const long long plane_vecs = plane_elems / N;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long plane = item / chunks_per_plane;
+        const long long chunk = item - plane * chunks_per_plane;
+        const S bias = b ? to_acc<T>(b[plane % p.size_b]) : (S)0;
+        const long long vbase = plane * plane_vecs;                       // first vector of the plane
+        const long long v0 = chunk * (256 * UNROLL) + threadIdx.x;       // vector index inside the plane
+        S vx[UNROLL][N];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (v0 + u * 256 < plane_vecs) load_vec((const T*)p.x, vbase + v0 + u * 256, vx[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long vi = v0 + u * 256;
+            if (vi >= plane_vecs) continue;
+            const long long v = vbase + vi;
+            S exr[N], eyr[N], edy[N], out[N];
+            if (p.xref) load_vec((const T*)p.xref, v, exr);
+            if (p.yref) load_vec((const T*)p.yref, v, eyr);
+            if (p.dy) load_vec((const T*)p.dy, v, edy);
+#pragma unroll
+            for (int j = 0; j < N; ++j)
+                out[j] = eval<S, A>(vx[u][j], bias, p.xref ? exr[j] : (S)0, p.yref ? eyr[j] : (S)0, p.dy ? edy[j] : (S)1, G, alpha, gain, clamp);
+            store_vec((T*)p.y, v, out);
+        }
+    }
+}
+
 template <typename T, int A>
 static int launch_bias_act(const BiasActArgs& p, cudaStream_t st) {
     constexpr int UNROLL = 4;
@@ -164,7 +240,21 @@ static int launch_bias_act(const BiasActArgs& p, cudaStream_t st) {
     const long long cap = (long long)sm_count() * 8;            // 8 resident blocks of 256 threads per SM
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    bias_act_kernel<T, A, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(p);
+    int bmode = 0;
+    if (p.b != nullptr) bmode = (p.step_b % N == 0) ? 1 : ((p.step_b == 1 && p.size_b % N == 0) ? 2 : 3);
+    // planar fast path: whole planes of >= 1024 elements share one bias (or there is no bias at all)
+    const long long plane_elems = (p.b == nullptr) ? p.size_x : p.step_b;
+    if ((p.b == nullptr || bmode == 1) && plane_elems >= 1024 && plane_elems % N == 0 && p.size_x % plane_elems == 0) {
+        const long long cpp = ceil_div<long long>(plane_elems / N, 256ll * UNROLL);
+        const long long items = (p.size_x / plane_elems) * cpp;
+        long long g = items < cap ? items : cap;
+        if (p.grad == 0) bias_act_planar_kernel<T, A, UNROLL, true><<<(unsigned)g, 256, 0, st>>>(p, plane_elems, cpp, items);
+        else bias_act_planar_kernel<T, A, UNROLL, false><<<(unsigned)g, 256, 0, st>>>(p, plane_elems, cpp, items);
+        IDE3D_CHECK_LAUNCH("bias_act_planar_kernel");
+        return IDE3D_OK;
+    }
+    if (p.grad == 0) bias_act_kernel<T, A, UNROLL, true><<<(unsigned)blocks, 256, 0, st>>>(p, bmode);
+    else bias_act_kernel<T, A, UNROLL, false><<<(unsigned)blocks, 256, 0, st>>>(p, bmode);
     IDE3D_CHECK_LAUNCH("bias_act_kernel");
     return IDE3D_OK;
 }

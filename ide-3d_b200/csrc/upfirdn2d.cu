@@ -13,6 +13,9 @@
 //     padding (pad mod up) is a template parameter, so every tap -> window index is a constant and there
 //     are no divisions, no bounds checks and no wasted zero taps in the inner loop.
 //   * generic kernel: any strides (channels_last included), any filter, one thread per output.
+#include <cuda.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace ide3d {
@@ -67,6 +70,70 @@ struct Axis {
     static_assert((kPatch * D) % U == 0, "patch origin must stay phase aligned");
 };
 
+// 4x4 output patch of this thread from the staged input tile (row pitch PITCH), polyphase indices all compile-time
+template <typename T, typename TT, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, int PITCH>
+__device__ __forceinline__ void patch_compute_store_impl(const UpfirArgs& p, const TT* __restrict__ tile,
+                                                         const typename AccT<T>::type (&fk)[FH][FW], int n, int c, int ox_t, int oy_t) {
+    using S = typename AccT<T>::type;
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    constexpr int TIWP = PITCH;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const TT* wbase = tile + (ty * AY::kStep) * TIWP + tx * AX::kStep;
+    S acc[kPatch][kPatch];
+#pragma unroll
+    for (int i = 0; i < kPatch; ++i)
+#pragma unroll
+        for (int j = 0; j < kPatch; ++j) acc[i][j] = 0;
+
+#pragma unroll
+    for (int r = 0; r < AY::kWin; ++r) {
+        S win[AX::kWin];
+#pragma unroll
+        for (int q = 0; q < AX::kWin; ++q) win[q] = ld<TT>(wbase + r * TIWP + q);
+#pragma unroll
+        for (int i = 0; i < kPatch; ++i) {
+#pragma unroll
+            for (int ty_ = 0; ty_ < AY::taps(i); ++ty_) {
+                if (AY::off(i) - AY::lo() + ty_ != r) continue;              // folded at compile time
+                const int ky = AY::k0(i) + ty_ * UY;
+#pragma unroll
+                for (int j = 0; j < kPatch; ++j)
+#pragma unroll
+                    for (int tx_ = 0; tx_ < AX::taps(j); ++tx_)
+                        acc[i][j] += fk[ky][AX::k0(j) + tx_ * UX] * win[AX::off(j) - AX::lo() + tx_];
+            }
+        }
+    }
+
+    const int ox0 = ox_t + tx * kPatch, oy0 = oy_t + ty * kPatch;
+    T* yout = (T*)p.y + n * p.osn + c * p.osc;
+#pragma unroll
+    for (int i = 0; i < kPatch; ++i) {
+        const int oy = oy0 + i;
+        if (oy >= p.out_h) break;
+        T* rowp = yout + oy * p.osh + ox0;
+        if (sizeof(T) == 4 && ox0 + kPatch <= p.out_w && ((reinterpret_cast<uintptr_t>(rowp) & 15) == 0)) {
+            __stcs(reinterpret_cast<float4*>(rowp), make_float4((float)acc[i][0], (float)acc[i][1], (float)acc[i][2], (float)acc[i][3]));
+        } else {
+#pragma unroll
+            for (int j = 0; j < kPatch; ++j)
+                if (ox0 + j < p.out_w) st<T>(rowp + j, acc[i][j]);
+        }
+    }
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, int PITCH>
+__device__ __forceinline__ void patch_compute_store(const UpfirArgs& p, const typename AccT<T>::type* __restrict__ tile,
+                                                    const typename AccT<T>::type (&fk)[FH][FW], int n, int c, int ox_t, int oy_t) {
+    patch_compute_store_impl<T, typename AccT<T>::type, UX, UY, DX, DY, FW, FH, PHX, PHY, PITCH>(p, tile, fk, n, c, ox_t, oy_t);
+}
+template <int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, int PITCH>
+__device__ __forceinline__ void patch_compute_store_h(const UpfirArgs& p, const __half* __restrict__ tile, const float (&fk)[FH][FW],
+                                                      int n, int c, int ox_t, int oy_t) {
+    patch_compute_store_impl<__half, __half, UX, UY, DX, DY, FW, FH, PHX, PHY, PITCH>(p, tile, fk, n, c, ox_t, oy_t);
+}
+
 template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
 __global__ void __launch_bounds__(256) upfirdn2d_patch_kernel(const UpfirArgs p, int tiles_x, int tiles_y) {
     using S = typename AccT<T>::type;
@@ -110,49 +177,104 @@ __global__ void __launch_bounds__(256) upfirdn2d_patch_kernel(const UpfirArgs p,
         }
         __syncthreads();
 
-        const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-        const S* wbase = tile + (ty * AY::kStep) * TIWP + tx * AX::kStep;
-        S acc[kPatch][kPatch];
-#pragma unroll
-        for (int i = 0; i < kPatch; ++i)
-#pragma unroll
-            for (int j = 0; j < kPatch; ++j) acc[i][j] = 0;
+        patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, TIWP>(p, tile, fk, n, c, ox_t, oy_t);
+    }
+}
 
-#pragma unroll
-        for (int r = 0; r < AY::kWin; ++r) {
-            S win[AX::kWin];
-#pragma unroll
-            for (int q = 0; q < AX::kWin; ++q) win[q] = wbase[r * TIWP + q];
-#pragma unroll
-            for (int i = 0; i < kPatch; ++i) {
-#pragma unroll
-                for (int ty_ = 0; ty_ < AY::taps(i); ++ty_) {
-                    if (AY::off(i) - AY::lo() + ty_ != r) continue;              // folded at compile time
-                    const int ky = AY::k0(i) + ty_ * UY;
-#pragma unroll
-                    for (int j = 0; j < kPatch; ++j)
-#pragma unroll
-                        for (int tx_ = 0; tx_ < AX::taps(j); ++tx_)
-                            acc[i][j] += fk[ky][AX::k0(j) + tx_ * UX] * win[AX::off(j) - AX::lo() + tx_];
-                }
-            }
-        }
+// ------------------------------------------------------------------------------------------
+// TMA-staged flavour of the patch kernel (fp32 / fp16, dense NCHW): the input tile is fetched by ONE
+// cp.async.bulk.tensor (3-D map: W x H x planes, box = tile), out-of-image elements are zero-filled by the TMA unit
+// (negative / overflowing coordinates included), two tiles are in flight per block (double buffer + mbarrier) so the
+// load of tile i+1 overlaps the FIR of tile i, and no thread spends instructions on staging.
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tma_bar_init(unsigned long long* bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_tile(void* dst, const CUtensorMap* map, unsigned long long* bar, int x, int y, int z, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(x), "r"(y), "r"(z) : "memory");
+}
+__device__ __forceinline__ void tma_bar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(ok) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+    }
+}
 
-        const int ox0 = ox_t + tx * kPatch, oy0 = oy_t + ty * kPatch;
-        T* yout = (T*)p.y + n * p.osn + c * p.osc;
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+struct TmaGeom {
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    static constexpr int kVec = 16 / (int)sizeof(T);                                   // box rows are whole 16-byte units
+    static constexpr int BW = (AX::kTileIn + kVec - 1) / kVec * kVec, BH = AY::kTileIn;
+    static constexpr int kTileBytes = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
+    static constexpr int kSmem = 2 * kTileBytes + 128 + 128;                           // 2 tiles + barriers + alignment slack
+};
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+__global__ void __launch_bounds__(256) upfirdn2d_patch_tma_kernel(const UpfirArgs p, int tiles_x, int tiles_y,
+                                                                  const __grid_constant__ CUtensorMap tmap) {
+    using GM = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    using AX = typename GM::AX;
+    using AY = typename GM::AY;
+    static_assert(sizeof(T) == sizeof(typename AccT<T>::type) || sizeof(T) == 2, "fp32 / fp16 only");
+    extern __shared__ unsigned char tma_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw) + 127) & ~(uintptr_t)127);
+    T* tiles[2] = {reinterpret_cast<T*>(base), reinterpret_cast<T*>(base + GM::kTileBytes)};
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + 2 * GM::kTileBytes);
+
+    float fk[FH][FW];
 #pragma unroll
-        for (int i = 0; i < kPatch; ++i) {
-            const int oy = oy0 + i;
-            if (oy >= p.out_h) break;
-            T* rowp = yout + oy * p.osh + ox0;
-            if (sizeof(T) == 4 && ox0 + kPatch <= p.out_w && ((reinterpret_cast<uintptr_t>(rowp) & 15) == 0)) {
-                __stcs(reinterpret_cast<float4*>(rowp), make_float4((float)acc[i][0], (float)acc[i][1], (float)acc[i][2], (float)acc[i][3]));
-            } else {
+    for (int ky = 0; ky < FH; ++ky)
 #pragma unroll
-                for (int j = 0; j < kPatch; ++j)
-                    if (ox0 + j < p.out_w) st<T>(rowp + j, acc[i][j]);
-            }
+        for (int kx = 0; kx < FW; ++kx) {
+            const int sy = p.flip ? ky : FH - 1 - ky, sx = p.flip ? kx : FW - 1 - kx;
+            fk[ky][kx] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
         }
+    const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);
+    const long long tiles_plane = (long long)tiles_x * tiles_y;
+    const long long total = tiles_plane * p.in_c * p.in_n;
+    constexpr unsigned kBytes = GM::BW * GM::BH * sizeof(T);
+
+    auto coords = [&](long long blk, int& plane, int& ox_t, int& oy_t) {
+        const long long pl = blk / tiles_plane;
+        const int t = (int)(blk - pl * tiles_plane);
+        plane = (int)pl;
+        ox_t = (t % tiles_x) * kTile; oy_t = (t / tiles_x) * kTile;
+    };
+    if (threadIdx.x == 0) {
+        tma_bar_init(&bars[0]); tma_bar_init(&bars[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((long long)blockIdx.x < total) {
+            int pl, ox_t, oy_t;
+            coords(blockIdx.x, pl, ox_t, oy_t);
+            tma_load_tile(tiles[0], &tmap, &bars[0], ox_t * DX / UX - ax + AX::lo(), oy_t * DY / UY - ay + AY::lo(), pl, kBytes);
+        }
+    }
+    __syncthreads();
+
+    int it = 0;
+    for (long long blk = blockIdx.x; blk < total; blk += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const long long nxt = blk + gridDim.x;
+        if (threadIdx.x == 0 && nxt < total) {            // buffer cur^1 was released by the __syncthreads ending the previous iteration
+            int pl, ox_t, oy_t;
+            coords(nxt, pl, ox_t, oy_t);
+            tma_load_tile(tiles[cur ^ 1], &tmap, &bars[cur ^ 1], ox_t * DX / UX - ax + AX::lo(), oy_t * DY / UY - ay + AY::lo(), pl, kBytes);
+        }
+        int plane, ox_t, oy_t;
+        coords(blk, plane, ox_t, oy_t);
+        const int n = plane / p.in_c, c = plane - n * p.in_c;
+        tma_bar_wait(&bars[cur], (it >> 1) & 1);
+        if constexpr (sizeof(T) == 4) {
+            patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const float*>(tiles[cur]), fk, n, c, ox_t, oy_t);
+        } else {
+            // fp16: widen the staged tile in place is not possible (same buffer); convert through registers in the window loads
+            patch_compute_store_h<UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const __half*>(tiles[cur]), fk, n, c, ox_t, oy_t);
+        }
+        __syncthreads();
     }
 }
 
@@ -188,8 +310,72 @@ __global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(const UpfirArgs 
     }
 }
 
+// ---- host side of the TMA path -----------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) return nullptr;
+        return (EncodeTiledFn)ptr;
+    }();
+    return fn;
+}
+
+// can the TMA unit describe this input?  dense NCHW (planes equally spaced), 16-byte aligned base and row pitch
+template <typename T>
+static bool tma_eligible(const UpfirArgs& p) {
+    if (sizeof(T) > 4 || encode_tiled() == nullptr) return false;
+    if (p.isw != 1 || p.osw != 1) return false;
+    if (p.isn != p.isc * p.in_c) return false;                           // (n, c) must collapse into one plane index
+    if ((reinterpret_cast<uintptr_t>(p.x) & 15) || (p.ish * sizeof(T)) % 16 || (p.isc * sizeof(T)) % 16) return false;
+    if ((long long)p.in_c * p.in_n > 0x7fffffffll) return false;
+    return true;
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+static int launch_patch_tma(const UpfirArgs& p, cudaStream_t st_) {
+    using GM = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    CUtensorMap map;
+    const cuuint64_t dims[3] = {(cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.in_c * p.in_n};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.ish * sizeof(T), (cuuint64_t)p.isc * sizeof(T)};
+    const cuuint32_t box[3] = {(cuuint32_t)GM::BW, (cuuint32_t)GM::BH, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode_tiled()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3,
+                                      const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    auto kern = upfirdn2d_patch_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    const size_t smem = GM::kSmem;
+    if (smem > 48 * 1024) IDE3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = ceil_div(p.out_w, kTile), tiles_y = ceil_div(p.out_h, kTile);
+    const long long total = (long long)tiles_x * tiles_y * p.in_c * p.in_n;
+    int per_sm = 1;
+    IDE3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, 256, smem, st_>>>(p, tiles_x, tiles_y, map);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_patch_tma_kernel");
+    return IDE3D_OK;
+}
+
 template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
 static int launch_patch(const UpfirArgs& p, cudaStream_t st_) {
+    if constexpr (sizeof(T) <= 4) {
+        // One bulk-tensor copy per tile; boxes beyond 48 KB (the down=2 tiles) stay on the thread-staged kernel.
+        constexpr bool small_box = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kTileBytes <= 48 * 1024;
+        // ROUND-1 STATUS: the TMA flavour is opt-in (IDE3D_TMA=1).  On the B200 box compute-sanitizer reports "Illegal
+        // instruction" at the UTMALDG of some blocks (profiles/r01_tma_upfirdn2d_fault.txt); until that is understood the
+        // validated thread-staged kernel below is what runs.
+        const char* tma_env = getenv("IDE3D_TMA");
+        if (small_box && tma_env != nullptr && tma_env[0] == '1' && tma_eligible<T>(p)) {
+            const int rc = launch_patch_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY>(p, st_);
+            if (rc != IDE3D_UNSUPPORTED) return rc;
+        }
+    }
     using S = typename AccT<T>::type;
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;

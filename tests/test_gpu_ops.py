@@ -156,6 +156,48 @@ def test_filtered_lrelu_golden():
         assert_close(fl.filtered_lrelu(x, fu=fu, fd=fd, b=b, **kw), g[k], 2e-5, what=k)
 
 
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 3e-5, 0), (torch.float16, 2e-2, 2e-2)])
+@pytest.mark.parametrize('hw', [(64, 64), (50, 37)])
+def test_filtered_lrelu_fused_shapes(dtype, atol, rtol, hw):
+    """The fused separable kernel on tile-unfriendly sizes / odd paddings / both flip settings, vs the oracle."""
+    from ide3d_b200 import _plugins
+    from ide3d_b200.torch_utils.ops import filtered_lrelu as fl
+    g = torch.Generator().manual_seed(8)
+    x = (torch.randn(2, 3, *hw, generator=g) * 2).to(dtype)
+    b = torch.randn(3, generator=g).to(dtype)
+    f12 = oops.setup_filter(np.hanning(14)[1:-1].tolist())
+    f8 = oops.setup_filter(np.hanning(10)[1:-1].tolist())
+    f24 = oops.setup_filter(np.hanning(26)[1:-1].tolist())
+    cases = [dict(fu=f12, fd=f12, up=2, down=2, padding=[10, 11, 10, 11], clamp=1.5),
+             dict(fu=f12, fd=f12, up=2, down=2, padding=[5, 6, 4, 7], clamp=None, flip_filter=True, gain=0.9, slope=0.3),
+             dict(fu=f8, fd=f8, up=2, down=2, padding=[3, 4, 3, 4], clamp=2.0),
+             dict(fu=f24, fd=f12, up=4, down=2, padding=[17, 18, 17, 18], clamp=0.8),
+             dict(fu=f12, fd=None, up=2, down=1, padding=[5, 6, 5, 6], clamp=1.0),
+             dict(fu=None, fd=f12, up=1, down=2, padding=[5, 6, 5, 6], clamp=1.0),
+             dict(fu=None, fd=None, up=1, down=1, padding=0, clamp=0.5)]
+    for kw in cases:
+        ref = oops.filtered_lrelu(x.float(), b=b.float(), **kw)
+        kd = {k: (v.to(DEV) if isinstance(v, torch.Tensor) else v) for k, v in kw.items()}
+        y = fl.filtered_lrelu(x.to(DEV), b=b.to(DEV), **kd)
+        assert y.dtype == dtype and y.shape == ref.shape
+        assert_close(y, ref, atol, rtol, what=str({k: v for k, v in kw.items() if not isinstance(v, torch.Tensor)}))
+    # the fused kernel really ran for the separable case (return code 0), and 2-D filters report "no kernel" (-1)
+    xd, bd = x.float().to(DEV), b.float().to(DEV)
+    y, so, rc = _plugins.filtered_lrelu(xd, f12.to(DEV), f12.to(DEV), bd, None, 2, 2, 10, 11, 10, 11, 0, 0, 1.4, 0.2, 1.5, False, True)
+    assert rc == 0 and so is not None
+    _, packed = oops.filtered_lrelu(x.float(), fu=f12, fd=f12, b=b.float(), up=2, down=2, padding=[10, 11, 10, 11], gain=1.4, slope=0.2, clamp=1.5, return_signs=True)
+    sh, swb = so.shape[2], so.shape[3]
+    # compare the 2-bit codes inside the active region (rows/cols the down-FIR actually reads)
+    def unpack(t):
+        t = t.cpu().to(torch.int32)
+        return torch.stack([(t >> (2 * i)) & 3 for i in range(4)], -1).reshape(*t.shape[:-1], -1)
+    mine, ref_codes = unpack(so), unpack(packed)
+    sw_active = y.shape[3] * 2 - 1 + 11
+    assert torch.equal(mine[:, :, :sh, :sw_active], ref_codes[:, :, :sh, :sw_active])
+    f2d = torch.outer(f8, f8).to(DEV)
+    assert _plugins.filtered_lrelu(xd, f2d, f2d, bd, None, 2, 2, 7, 8, 7, 8, 0, 0, 1.4, 0.2, 1.5, False, False)[2] == -1
+
+
 def test_filtered_lrelu_act_sign_tensor_and_backward():
     from ide3d_b200 import _plugins
     from ide3d_b200.torch_utils.ops import filtered_lrelu as fl
