@@ -134,13 +134,16 @@ __device__ __forceinline__ void patch_compute_store_h(const UpfirArgs& p, const 
     patch_compute_store_impl<__half, __half, UX, UY, DX, DY, FW, FH, PHX, PHY, PITCH>(p, tile, fk, n, c, ox_t, oy_t);
 }
 
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+// kVec (fp32, 16-byte aligned rows, W % 4 == 0): the tile is staged with LDG.128 from the 4-aligned column at or before
+// the tile origin; the 0..3 surplus columns are absorbed by the row pitch and the window base is shifted accordingly.
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kVec>
 __global__ void __launch_bounds__(256) upfirdn2d_patch_kernel(const UpfirArgs p, int tiles_x, int tiles_y) {
     using S = typename AccT<T>::type;
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
     constexpr int TIW = AX::kTileIn, TIH = AY::kTileIn;
-    constexpr int TIWP = TIW | 1;                            // odd row pitch: spreads rows over banks
+    constexpr int TIWP = (kVec ? ((TIW + 3 + 3) / 4 * 4) : TIW) | 1;   // odd row pitch: spreads rows over banks
+    constexpr int TIV = (TIW + 3 + 3) / 4;                   // float4 per staged row in the vector path
     extern __shared__ __align__(16) unsigned char smem_raw[];
     S* tile = reinterpret_cast<S*>(smem_raw);
 
@@ -168,16 +171,31 @@ __global__ void __launch_bounds__(256) upfirdn2d_patch_kernel(const UpfirArgs p,
         const T* xin = (const T*)p.x + n * p.isn + c * p.isc;
 
         __syncthreads();                                      // previous tile fully consumed
-        for (int i = threadIdx.x; i < TIW * TIH; i += 256) {
-            const int ty = i / TIW, tx = i - ty * TIW;
-            const int gx = ix_t + tx, gy = iy_t + ty;
-            S v = 0;
-            if ((unsigned)gx < (unsigned)p.in_w && (unsigned)gy < (unsigned)p.in_h) v = ld<T>(xin + gy * p.ish + gx);
-            tile[ty * TIWP + tx] = v;
+        int shift = 0;
+        if constexpr (kVec) {
+            const int ixa = ix_t & ~3;                        // 4-aligned column at or left of the tile origin (also for negatives)
+            shift = ix_t - ixa;
+            for (int i = threadIdx.x; i < TIV * TIH; i += 256) {
+                const int ty = i / TIV, tv = i - ty * TIV;
+                const int gx = ixa + tv * 4, gy = iy_t + ty;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if ((unsigned)gx < (unsigned)p.in_w && (unsigned)gy < (unsigned)p.in_h)    // W % 4 == 0: a vector is all in or all out
+                    v = __ldg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(xin) + gy * p.ish + gx));
+                S* d = tile + ty * TIWP + tv * 4;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            for (int i = threadIdx.x; i < TIW * TIH; i += 256) {
+                const int ty = i / TIW, tx = i - ty * TIW;
+                const int gx = ix_t + tx, gy = iy_t + ty;
+                S v = 0;
+                if ((unsigned)gx < (unsigned)p.in_w && (unsigned)gy < (unsigned)p.in_h) v = ld<T>(xin + gy * p.ish + gx);
+                tile[ty * TIWP + tx] = v;
+            }
         }
         __syncthreads();
 
-        patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, TIWP>(p, tile, fk, n, c, ox_t, oy_t);
+        patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, TIWP>(p, tile + shift, fk, n, c, ox_t, oy_t);
     }
 }
 
@@ -379,8 +397,13 @@ static int launch_patch(const UpfirArgs& p, cudaStream_t st_) {
     using S = typename AccT<T>::type;
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
-    const size_t smem = (size_t)(AX::kTileIn | 1) * AY::kTileIn * sizeof(S);
-    auto kern = upfirdn2d_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    bool vec = false;
+    if constexpr (sizeof(T) == 4)
+        vec = (p.in_w % 4 == 0) && (p.ish % 4 == 0) && (p.isc % 4 == 0) && (p.isn % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.x) & 15) == 0);
+    const int pitch = (vec ? ((AX::kTileIn + 6) / 4 * 4) : AX::kTileIn) | 1;
+    const size_t smem = (size_t)pitch * AY::kTileIn * sizeof(S) + 16;
+    void (*kern)(const UpfirArgs, int, int) = upfirdn2d_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, false>;
+    if constexpr (sizeof(T) == 4) { if (vec) kern = upfirdn2d_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, true>; }
     if (smem > 48 * 1024) IDE3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_x = ceil_div(p.out_w, kTile), tiles_y = ceil_div(p.out_h, kTile);
     const long long total = (long long)tiles_x * tiles_y * p.in_c * p.in_n;
@@ -408,6 +431,56 @@ static int dispatch_phase(const UpfirArgs& p, cudaStream_t s) {
         return launch_patch<T, 2, 2, DX, DY, FW, FH, 1, 1>(p, s);
     }
     IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: no phase table");
+}
+
+// ------------------------------------------------------------------------------------------
+// channels_last flavour (stride_c == 1): a thread owns one output pixel x 4 consecutive channels (one 16-byte vector for
+// fp32, 8 bytes for fp16), walks the live polyphase taps and reads the neighbouring input pixels straight from L1/L2
+// (adjacent outputs share them).  Any filter / factors; coalesced along C.
+template <typename T>
+__global__ void __launch_bounds__(256) upfirdn2d_cl_kernel(const UpfirArgs p) {
+    using S = typename AccT<T>::type;
+    const int c4n = p.in_c >> 2;
+    const long long total = (long long)p.out_w * p.out_h * p.in_n * c4n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(i % c4n);
+        long long r = i / c4n;
+        const int ox = (int)(r % p.out_w); r /= p.out_w;
+        const int oy = (int)(r % p.out_h);
+        const int n = (int)(r / p.out_h);
+        const int bx = ox * p.dx - p.px0, by = oy * p.dy - p.py0;
+        const int kx0 = ((-bx) % p.ux + p.ux) % p.ux, ky0 = ((-by) % p.uy + p.uy) % p.uy;
+        const T* xin = (const T*)p.x + n * p.isn + c4 * 4;
+        S a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int ky = ky0; ky < p.fh; ky += p.uy) {
+            if (by + ky < 0) continue;
+            const int iy = (by + ky) / p.uy;
+            if (iy >= p.in_h) break;
+            const int sy = p.flip ? ky : p.fh - 1 - ky;
+            for (int kx = kx0; kx < p.fw; kx += p.ux) {
+                if (bx + kx < 0) continue;
+                const int ix = (bx + kx) / p.ux;
+                if (ix >= p.in_w) break;
+                const S w = (S)p.f[sy * p.fsh + (p.flip ? kx : p.fw - 1 - kx) * p.fsw];
+                const T* px = xin + iy * p.ish + ix * p.isw;
+                a0 += w * ld<T>(px); a1 += w * ld<T>(px + 1); a2 += w * ld<T>(px + 2); a3 += w * ld<T>(px + 3);
+            }
+        }
+        T* py = (T*)p.y + n * p.osn + oy * p.osh + ox * p.osw + c4 * 4;
+        const S g = (S)p.gain;
+        st<T>(py, a0 * g); st<T>(py + 1, a1 * g); st<T>(py + 2, a2 * g); st<T>(py + 3, a3 * g);
+    }
+}
+
+template <typename T>
+static int launch_cl(const UpfirArgs& p, cudaStream_t s) {
+    const long long total = (long long)p.out_w * p.out_h * p.in_n * (p.in_c >> 2);
+    long long grid = ceil_div<long long>(total, 256);
+    const long long cap = (long long)sm_count() * 16;
+    if (grid > cap) grid = cap;
+    upfirdn2d_cl_kernel<T><<<(unsigned)grid, 256, 0, s>>>(p);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_cl_kernel");
+    return IDE3D_OK;
 }
 
 template <typename T>
@@ -440,6 +513,7 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
         IDE3D_CASE(1, 1, 1, 1, 1, 12)
 #undef IDE3D_CASE
     }
+    if (p.isc == 1 && p.osc == 1 && (p.in_c & 3) == 0 && p.isw != 1) return launch_cl<T>(p, s);
     return launch_generic<T>(p, s);
 }
 

@@ -261,3 +261,16 @@ def test_plugin_loader_contract(capsys):
         custom_ops.get_plugin('no_such_plugin')
     with pytest.raises(RuntimeError, match='f must be float32'):
         p.upfirdn2d(torch.zeros(1, 1, 4, 4, device=DEV), torch.ones(2, 2, device=DEV, dtype=torch.float64), 1, 1, 1, 1, 0, 0, 0, 0, False, 1.0)
+
+
+def test_upfirdn2d_channels_last_kernel_matches_contiguous_bitwise_shape():
+    """channels_last inputs take the 4-channel-vector kernel (C % 4 == 0) and keep the memory format."""
+    from ide3d_b200.torch_utils.ops import upfirdn2d as up
+    g = torch.Generator().manual_seed(12)
+    x = torch.randn(2, 8, 33, 20, generator=g)
+    f = oops.setup_filter([1, 3, 3, 1])
+    xc = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    for fn, ref in ((up.upsample2d, oops.upsample2d), (up.downsample2d, oops.downsample2d), (up.filter2d, oops.filter2d)):
+        y = fn(xc, f.to(DEV))
+        assert y.is_contiguous(memory_format=torch.channels_last)
+        assert_close(y, ref(x, f), 1e-5)
