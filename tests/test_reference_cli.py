@@ -1,0 +1,108 @@
+"""CPU, build container only: the reference's OWN caller scripts (gen_images.py, gen_videos.py, extract_shapes.py --
+imported unmodified from /root/reference) run against this package through `compat.install()`.
+
+What is stubbed, and why it does not touch the contract under test:
+  * `legacy.load_network_pkl`  -> returns a small random-init TriPlaneGenerator (no checkpoint pickle exists offline)
+  * `dnnlib.util.open_url`     -> dummy context manager (the "pickle path" is never read)
+  * imageio / mrcfile / plyfile / skimage -> absent output-writer dependencies of the scripts
+  * torch.device('cuda') inside the scripts -> 'cpu', and the CUDA entry points -> oracle (no GPU in this container)
+  * torchvision's save_image   -> recorder (the scripts call it with the removed `range=` keyword)
+Skipped on machines without /root/reference (the GPU box)."""
+
+import contextlib
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REF = '/root/reference'
+pytestmark = pytest.mark.skipif(not os.path.isdir(REF), reason='reference tree not present')
+
+
+@pytest.fixture()
+def ref_env(monkeypatch):
+    from oracle.backend import cpu_reference_ops
+    import ide3d_b200.compat as compat
+    from ide3d_b200.training.triplane import TriPlaneGenerator
+
+    saved = dict(sys.modules)
+    monkeypatch.syspath_prepend(REF)
+    monkeypatch.setattr(sys, 'dont_write_bytecode', True)
+    for name in ('imageio', 'mrcfile', 'plyfile', 'skimage', 'skimage.measure'):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules['skimage'].measure = sys.modules['skimage.measure']
+    compat.install()                                     # training.*, torch_utils.* -> this package
+
+    torch.manual_seed(0)
+    G = TriPlaneGenerator(z_dim=32, w_dim=32, img_resolution=64, plane_resolution=32, render_size=16, channel_base=512,
+                          channel_max=16, sr_channels=(8, 8), mapping_kwargs=dict(num_layers=2)).eval().requires_grad_(False)
+    legacy = types.ModuleType('legacy')
+    legacy.load_network_pkl = lambda f: {'G_ema': G}
+    monkeypatch.setitem(sys.modules, 'legacy', legacy)
+    import dnnlib                                        # the reference's own dnnlib (EasyDict, seg_tools, util.open_url)
+    monkeypatch.setattr(dnnlib.util, 'open_url', lambda *a, **k: contextlib.nullcontext(None))
+
+    real_device = torch.device
+
+    class _Dev:                                          # scripts hard-code torch.device('cuda')
+        def __call__(self, *a, **k):
+            return real_device('cpu')
+
+    with cpu_reference_ops():
+        yield G, _Dev()
+    ours = {'training', 'torch_utils', 'dnnlib', 'legacy', 'gen_images', 'gen_videos', 'extract_shapes', 'camera_utils'}
+    for k in list(sys.modules):                          # drop only what this fixture introduced (cv2 & co. cannot re-import)
+        if k not in saved and k.split('.')[0] in ours:
+            del sys.modules[k]
+    for k in ours:
+        if k in saved:
+            sys.modules[k] = saved[k]
+
+
+def test_gen_images_runs_unchanged(ref_env, tmp_path, monkeypatch):
+    G, dev = ref_env
+    gen_images = importlib.import_module('gen_images')
+    saved_imgs = {}
+    monkeypatch.setattr(gen_images, 'save_image', lambda t, path, **kw: saved_imgs.__setitem__(os.path.basename(path), t.clone()))
+    monkeypatch.setattr(gen_images.torch, 'device', dev)
+    try:
+        gen_images.generate_images.callback(network_pkl='unused.pkl', seeds=[3], truncation_psi=0.7, noise_mode='const', outdir=str(tmp_path))
+    finally:
+        monkeypatch.undo()
+    assert set(saved_imgs) == {'seed0003.png', 'seed0003_seg.png'}
+    img, seg = saved_imgs['seed0003.png'], saved_imgs['seed0003_seg.png']
+    assert img.shape == (3, 3, 64, 64) and seg.shape == (3, 3, 64, 64)          # 3 yaws; mask2color gives RGB maps
+    assert torch.isfinite(img).all() and not torch.allclose(img[0], img[2])     # different yaws, different views
+
+
+def test_extract_shapes_block_walk_runs_unchanged(ref_env, monkeypatch):
+    G, dev = ref_env
+    es = importlib.import_module('extract_shapes')
+    z = torch.from_numpy(np.random.RandomState(0).randn(1, G.z_dim))
+    label = torch.tensor([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 2.7, 0, 0, 0, 1, 4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1])[None].float()
+    vox = es.sample_generator_ide3d(G, None, z.float(), label, cube_length=1.0, voxel_resolution=12, psi=0.7, max_batch=500,
+                                    h_stddev=0., v_stddev=0., num_steps=96)
+    assert vox.shape == (12, 12, 12) and np.isfinite(vox).all() and vox.std() > 0
+
+
+def test_gen_videos_frame_loop_runs_unchanged(ref_env, monkeypatch):
+    G, dev = ref_env
+    frames = []
+
+    class _Writer:
+        def append_data(self, a):
+            frames.append(np.asarray(a))
+
+        def close(self):
+            pass
+
+    sys.modules['imageio'].get_writer = lambda *a, **k: _Writer()
+    gv = importlib.import_module('gen_videos')
+    gv.gen_interp_video(G, 'unused.mp4', seeds=[0, 1], w_frames=2, grid_dims=(1, 1), psi=0.7, truncation_cutoff=4,
+                        image_mode='image_seg', device=torch.device('cpu'))
+    assert len(frames) == 4                                                      # 2 keyframes x 2 frames
+    assert frames[0].dtype == np.uint8 and frames[0].shape == (64, 128, 3)       # image | colourised mask, side by side
