@@ -60,6 +60,38 @@ def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
     return y
 
 
+def modconv_epilogue(x, scale, noise, b, act, alpha, gain, clamp):
+    """bias_act(x * scale[:, :, None, None] + noise, b) in one pass (extension, forward only).  x [N,C,H,W] dense NCHW or
+    channels_last; scale [N,C] | None; noise [H,W] / [1,1,H,W] / [N,1,H,W] | None; b [C] | None.  Returns None when the
+    kernel does not take the shape (caller composes the two reference ops instead)."""
+    L.require_cuda(x)
+    _req(x.ndim == 4, 'x must be rank 4')
+    n, c, h, w = x.shape
+    cl = (not x.is_contiguous()) and x.is_contiguous(memory_format=torch.channels_last)
+    _req(x.is_contiguous() or cl, 'x must be non-overlapping and dense')
+    vec = 16 // x.element_size()
+    if x.numel() == 0 or (cl and c % vec != 0) or (not cl and (h * w) % vec != 0):
+        return None
+    if _has(scale):
+        _req(scale.numel() == n * c, 'scale must have N*C elements')
+        scale = scale.to(dtype=x.dtype).reshape(n, c).contiguous()
+    noise_batch = 1
+    if _has(noise):
+        _req(noise.numel() in (h * w, n * h * w), 'noise must be [H,W] or [N,1,H,W]')
+        noise_batch = noise.numel() // (h * w)
+        noise = noise.to(dtype=x.dtype).contiguous()
+    if _has(b):
+        _req(b.ndim == 1 and b.shape[0] == c, 'b has wrong number of elements')
+        b = b.to(dtype=x.dtype).contiguous()
+    y = torch.empty_like(x)
+    rc = L.get_lib().ide3d_modconv_epilogue(L.ptr(x), L.ptr(scale) if _has(scale) else None, L.ptr(noise) if _has(noise) else None,
+                                            L.ptr(b) if _has(b) else None, L.ptr(y), L.dtype_code(x), int(act), float(alpha),
+                                            float(gain), float(clamp), n, c, h * w, noise_batch, int(cl), L.stream_ptr(x.device))
+    if L.check(rc, allow_unsupported=True) == L.UNSUPPORTED:
+        return None
+    return y
+
+
 # ------------------------------------------------------------------------------------------- upfirdn2d
 def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
     L.require_cuda(x, f)
@@ -174,7 +206,7 @@ class _Plugin:
 
 
 PLUGINS = {
-    'bias_act_plugin': _Plugin('bias_act_plugin', bias_act=bias_act),
+    'bias_act_plugin': _Plugin('bias_act_plugin', bias_act=bias_act, modconv_epilogue=modconv_epilogue),
     'upfirdn2d_plugin': _Plugin('upfirdn2d_plugin', upfirdn2d=upfirdn2d),
     'filtered_lrelu_plugin': _Plugin('filtered_lrelu_plugin', filtered_lrelu=filtered_lrelu,
                                      filtered_lrelu_act_=filtered_lrelu_act_),

@@ -299,3 +299,172 @@ extern "C" int ide3d_bias_act(const void* x, const void* b, const void* xref, co
     }
     IDE3D_FAIL(IDE3D_INVALID, "bias_act: unsupported dtype %d", dtype);
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// Fused epilogue of an activation-scaled ("non-fused") modulated convolution (inversion/networks.py:97-111 followed by
+// :512):   y = bias_act(x * scale[n,c] + noise[(n),h,w], b[c])   in ONE pass instead of fma.fma + bias_act (two).
+// No counterpart among the reference plugins; forward only (the Python wrapper composes the two reference ops whenever
+// autograd is involved).
+namespace ide3d {
+
+struct EpiArgs {
+    const void *x, *scale, *noise, *b;
+    void* y;
+    float alpha, gain, clamp;
+    long long n, c, hw;
+    int noise_batch;                      // 1: one noise map for the whole batch, n: one per sample
+};
+
+template <typename T> __device__ __forceinline__ void load_vec_keep(const T* p, long long v, typename Acc<T>::type (&o)[Vec<T>::N]);
+template <> __device__ __forceinline__ void load_vec_keep<float>(const float* p, long long v, float (&o)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p) + v);
+    o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w;
+}
+template <> __device__ __forceinline__ void load_vec_keep<double>(const double* p, long long v, double (&o)[2]) {
+    const double2 t = __ldg(reinterpret_cast<const double2*>(p) + v);
+    o[0] = t.x; o[1] = t.y;
+}
+template <> __device__ __forceinline__ void load_vec_keep<__half>(const __half* p, long long v, float (&o)[8]) {
+    const uint4 t = __ldg(reinterpret_cast<const uint4*>(p) + v);
+    const unsigned w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        o[2 * i] = f.x; o[2 * i + 1] = f.y;
+    }
+}
+
+// NCHW: (plane, chunk) work items, scale and bias are block-uniform, the noise map is read through L1/L2 (it is shared by
+// every channel of the sample).
+template <typename T, int A, int UNROLL>
+__global__ void __launch_bounds__(256) modconv_epilogue_planar_kernel(const EpiArgs p, long long chunks_per_plane, long long items) {
+    using S = typename Acc<T>::type;
+    constexpr int N = Vec<T>::N;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const long long plane_vecs = p.hw / N;
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const long long plane = item / chunks_per_plane;
+        const long long chunk = item - plane * chunks_per_plane;
+        const long long smp = plane / p.c;
+        const S d = p.scale ? to_acc<T>(((const T*)p.scale)[plane]) : (S)1;
+        const S bias = p.b ? to_acc<T>(((const T*)p.b)[plane - smp * p.c]) : (S)0;
+        const long long vbase = plane * plane_vecs;
+        const long long nbase = (p.noise_batch == 1 ? 0 : smp) * plane_vecs;
+        const long long v0 = chunk * (256 * UNROLL) + threadIdx.x;
+        S vx[UNROLL][N], vn[UNROLL][N];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (v0 + u * 256 < plane_vecs) {
+                load_vec((const T*)p.x, vbase + v0 + u * 256, vx[u]);
+                if (p.noise) load_vec_keep<T>((const T*)p.noise, nbase + v0 + u * 256, vn[u]);
+            }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long vi = v0 + u * 256;
+            if (vi >= plane_vecs) continue;
+            S out[N];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                const S t = p.noise ? vx[u][j] * d + vn[u][j] : vx[u][j] * d;
+                out[j] = eval<S, A>(t, bias, (S)0, (S)0, (S)1, 0, alpha, gain, clamp);
+            }
+            store_vec((T*)p.y, vbase + vi, out);
+        }
+    }
+}
+
+// channels_last: one 16-byte vector = N consecutive channels of one pixel; scale / bias are vectors, the noise a scalar.
+template <typename T, int A, int UNROLL>
+__global__ void __launch_bounds__(256) modconv_epilogue_cl_kernel(const EpiArgs p) {
+    using S = typename Acc<T>::type;
+    constexpr int N = Vec<T>::N;
+    const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
+    const long long nvec = p.n * p.hw * p.c / N;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const unsigned cv = (unsigned)(p.c / N);                     // vectors per pixel
+    for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
+        S vx[UNROLL][N];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            if (v0 + u * stride < nvec) load_vec((const T*)p.x, v0 + u * stride, vx[u]);
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long v = v0 + u * stride;
+            if (v >= nvec) continue;
+            const long long pix = v / cv;
+            const long long c0 = (v - pix * cv);                  // vector index inside the pixel
+            const long long smp = pix / p.hw;
+            S d[N], bb[N], out[N];
+            if (p.scale) load_vec_keep<T>((const T*)p.scale, smp * cv + c0, d);
+            if (p.b) load_vec_keep<T>((const T*)p.b, c0, bb);
+            const S nz = p.noise ? to_acc<T>(__ldg((const T*)p.noise + (p.noise_batch == 1 ? pix - smp * p.hw : pix))) : (S)0;
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                S t = p.scale ? vx[u][j] * d[j] : vx[u][j];
+                if (p.noise) t = p.scale ? vx[u][j] * d[j] + nz : vx[u][j] + nz;
+                out[j] = eval<S, A>(t, p.b ? bb[j] : (S)0, (S)0, (S)0, (S)1, 0, alpha, gain, clamp);
+            }
+            store_vec((T*)p.y, v, out);
+        }
+    }
+}
+
+template <typename T, int A>
+static int launch_epilogue(const EpiArgs& p, int channels_last, cudaStream_t st) {
+    constexpr int UNROLL = 4;
+    constexpr int N = Vec<T>::N;
+    const long long cap = (long long)sm_count() * 8;
+    if (channels_last) {
+        if (p.c % N != 0) IDE3D_FAIL(IDE3D_UNSUPPORTED, "modconv_epilogue: channels_last needs C %% %d == 0", N);
+        const long long nvec = p.n * p.hw * p.c / N;
+        long long blocks = ceil_div<long long>(nvec, 256ll * UNROLL);
+        if (blocks > cap) blocks = cap;
+        modconv_epilogue_cl_kernel<T, A, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(p);
+        IDE3D_CHECK_LAUNCH("modconv_epilogue_cl_kernel");
+        return IDE3D_OK;
+    }
+    if (p.hw % N != 0) IDE3D_FAIL(IDE3D_UNSUPPORTED, "modconv_epilogue: H*W must be a multiple of %d", N);
+    const long long cpp = ceil_div<long long>(p.hw / N, 256ll * UNROLL);
+    const long long items = p.n * p.c * cpp;
+    const long long g = items < cap ? items : cap;
+    modconv_epilogue_planar_kernel<T, A, UNROLL><<<(unsigned)g, 256, 0, st>>>(p, cpp, items);
+    IDE3D_CHECK_LAUNCH("modconv_epilogue_planar_kernel");
+    return IDE3D_OK;
+}
+
+template <typename T>
+static int dispatch_epilogue(const EpiArgs& p, int act, int channels_last, cudaStream_t st) {
+    switch (act) {
+        case 1: return launch_epilogue<T, 1>(p, channels_last, st);
+        case 2: return launch_epilogue<T, 2>(p, channels_last, st);
+        case 3: return launch_epilogue<T, 3>(p, channels_last, st);
+        case 4: return launch_epilogue<T, 4>(p, channels_last, st);
+        case 5: return launch_epilogue<T, 5>(p, channels_last, st);
+        case 6: return launch_epilogue<T, 6>(p, channels_last, st);
+        case 7: return launch_epilogue<T, 7>(p, channels_last, st);
+        case 8: return launch_epilogue<T, 8>(p, channels_last, st);
+        case 9: return launch_epilogue<T, 9>(p, channels_last, st);
+    }
+    IDE3D_FAIL(IDE3D_INVALID, "modconv_epilogue: unknown activation index %d", act);
+}
+
+}  // namespace ide3d
+
+extern "C" int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y, int dtype,
+                                      int act, float alpha, float gain, float clamp, int64_t n, int64_t c, int64_t hw,
+                                      int64_t noise_batch, int channels_last, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(n >= 0 && c >= 0 && hw >= 0, "modconv_epilogue: negative size");
+    if (n * c * hw == 0) return IDE3D_OK;
+    IDE3D_REQUIRE(x && y, "modconv_epilogue: null x/y");
+    IDE3D_REQUIRE(noise == nullptr || noise_batch == 1 || noise_batch == n, "modconv_epilogue: noise batch must be 1 or n");
+    const uintptr_t all = (uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)noise | (uintptr_t)b;
+    IDE3D_REQUIRE((all & 15) == 0, "modconv_epilogue: tensors must be 16-byte aligned");
+    ide3d::EpiArgs p{x, scale, noise, b, y, alpha, gain, clamp, n, c, hw, (int)noise_batch};
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case IDE3D_F32: return ide3d::dispatch_epilogue<float>(p, act, channels_last, st);
+        case IDE3D_F16: return ide3d::dispatch_epilogue<__half>(p, act, channels_last, st);
+        case IDE3D_F64: return ide3d::dispatch_epilogue<double>(p, act, channels_last, st);
+    }
+    IDE3D_FAIL(IDE3D_INVALID, "modconv_epilogue: unsupported dtype %d", dtype);
+}

@@ -225,8 +225,11 @@ template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, i
 struct TmaGeom {
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
-    static constexpr int kVec = 16 / (int)sizeof(T);                                   // box rows are whole 16-byte units
-    static constexpr int BW = (AX::kTileIn + kVec - 1) / kVec * kVec, BH = AY::kTileIn;
+    // The innermost box coordinate has to sit on a 16-byte boundary: UTMALDG raises "illegal instruction" for x = -1 or 31
+    // (fp32) while x = 0 or 64 work (scripts/tma_probe.cu, profiles/r01_tma_probe.txt).  The box therefore starts at the
+    // 16-byte aligned column at or left of the tile origin and is up to kVec-1 columns wider; the window base is shifted.
+    static constexpr int kVec = 16 / (int)sizeof(T);
+    static constexpr int BW = (AX::kTileIn + kVec - 1 + kVec - 1) / kVec * kVec, BH = AY::kTileIn;
     static constexpr int kTileBytes = ((BW * BH * (int)sizeof(T) + 127) / 128) * 128;
     static constexpr int kSmem = 2 * kTileBytes + 128 + 128;                           // 2 tiles + barriers + alignment slack
 };
@@ -238,6 +241,7 @@ __global__ void __launch_bounds__(256) upfirdn2d_patch_tma_kernel(const UpfirArg
     using AX = typename GM::AX;
     using AY = typename GM::AY;
     static_assert(sizeof(T) == sizeof(typename AccT<T>::type) || sizeof(T) == 2, "fp32 / fp16 only");
+    static_assert((kTile * DX / UX) % GM::kVec == 0, "tile origins must keep the 16-byte phase of the box origin");
     extern __shared__ unsigned char tma_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw) + 127) & ~(uintptr_t)127);
     T* tiles[2] = {reinterpret_cast<T*>(base), reinterpret_cast<T*>(base + GM::kTileBytes)};
@@ -262,14 +266,17 @@ __global__ void __launch_bounds__(256) upfirdn2d_patch_tma_kernel(const UpfirArg
         plane = (int)pl;
         ox_t = (t % tiles_x) * kTile; oy_t = (t / tiles_x) * kTile;
     };
+    // tile origins advance by kTile*DX/UX columns (a multiple of 16), so the distance to the aligned box origin is one constant
+    const int shift = (-ax + AX::lo()) & (GM::kVec - 1);
+    auto issue = [&](long long blk, int buf) {
+        int pl, ox_t, oy_t;
+        coords(blk, pl, ox_t, oy_t);
+        tma_load_tile(tiles[buf], &tmap, &bars[buf], ox_t * DX / UX - ax + AX::lo() - shift, oy_t * DY / UY - ay + AY::lo(), pl, kBytes);
+    };
     if (threadIdx.x == 0) {
         tma_bar_init(&bars[0]); tma_bar_init(&bars[1]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((long long)blockIdx.x < total) {
-            int pl, ox_t, oy_t;
-            coords(blockIdx.x, pl, ox_t, oy_t);
-            tma_load_tile(tiles[0], &tmap, &bars[0], ox_t * DX / UX - ax + AX::lo(), oy_t * DY / UY - ay + AY::lo(), pl, kBytes);
-        }
+        if ((long long)blockIdx.x < total) issue(blockIdx.x, 0);
     }
     __syncthreads();
 
@@ -277,20 +284,16 @@ __global__ void __launch_bounds__(256) upfirdn2d_patch_tma_kernel(const UpfirArg
     for (long long blk = blockIdx.x; blk < total; blk += gridDim.x, ++it) {
         const int cur = it & 1;
         const long long nxt = blk + gridDim.x;
-        if (threadIdx.x == 0 && nxt < total) {            // buffer cur^1 was released by the __syncthreads ending the previous iteration
-            int pl, ox_t, oy_t;
-            coords(nxt, pl, ox_t, oy_t);
-            tma_load_tile(tiles[cur ^ 1], &tmap, &bars[cur ^ 1], ox_t * DX / UX - ax + AX::lo(), oy_t * DY / UY - ay + AY::lo(), pl, kBytes);
-        }
+        if (threadIdx.x == 0 && nxt < total) issue(nxt, cur ^ 1);   // buffer cur^1 was released by the __syncthreads ending the previous iteration
         int plane, ox_t, oy_t;
         coords(blk, plane, ox_t, oy_t);
         const int n = plane / p.in_c, c = plane - n * p.in_c;
         tma_bar_wait(&bars[cur], (it >> 1) & 1);
         if constexpr (sizeof(T) == 4) {
-            patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const float*>(tiles[cur]), fk, n, c, ox_t, oy_t);
+            patch_compute_store<T, UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const float*>(tiles[cur]) + shift, fk, n, c, ox_t, oy_t);
         } else {
             // fp16: widen the staged tile in place is not possible (same buffer); convert through registers in the window loads
-            patch_compute_store_h<UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const __half*>(tiles[cur]), fk, n, c, ox_t, oy_t);
+            patch_compute_store_h<UX, UY, DX, DY, FW, FH, PHX, PHY, GM::BW>(p, reinterpret_cast<const __half*>(tiles[cur]) + shift, fk, n, c, ox_t, oy_t);
         }
         __syncthreads();
     }
@@ -383,13 +386,11 @@ static int launch_patch_tma(const UpfirArgs& p, cudaStream_t st_) {
 template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
 static int launch_patch(const UpfirArgs& p, cudaStream_t st_) {
     if constexpr (sizeof(T) <= 4) {
-        // One bulk-tensor copy per tile; boxes beyond 48 KB (the down=2 tiles) stay on the thread-staged kernel.
-        constexpr bool small_box = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kTileBytes <= 48 * 1024;
-        // ROUND-1 STATUS: the TMA flavour is opt-in (IDE3D_TMA=1).  On the B200 box compute-sanitizer reports "Illegal
-        // instruction" at the UTMALDG of some blocks (profiles/r01_tma_upfirdn2d_fault.txt); until that is understood the
-        // validated thread-staged kernel below is what runs.
+        // One bulk-tensor copy per tile, double-buffered: both tiles have to fit the 227 KB of one SM.  IDE3D_TMA=0 selects
+        // the thread-staged kernel below (kept for tensors the TMA unit cannot describe: unaligned base / row pitch).
+        constexpr bool fits = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kSmem <= 200 * 1024;
         const char* tma_env = getenv("IDE3D_TMA");
-        if (small_box && tma_env != nullptr && tma_env[0] == '1' && tma_eligible<T>(p)) {
+        if (fits && !(tma_env != nullptr && tma_env[0] == '0') && tma_eligible<T>(p)) {
             const int rc = launch_patch_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY>(p, st_);
             if (rc != IDE3D_UNSUPPORTED) return rc;
         }
@@ -434,7 +435,128 @@ static int dispatch_phase(const UpfirArgs& p, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------
-// channels_last flavour (stride_c == 1): a thread owns one output pixel x 4 consecutive channels (one 16-byte vector for
+// channels_last patch kernel (stride_c == 1, C % 4 == 0) for the StyleGAN2 4x4 filter shapes: a thread owns a 4x4 output
+// patch x 4 consecutive channels.  Same compile-time polyphase tables as the planar patch kernel; the input window
+// (kWin x kWin pixels, e.g. 7x7 for the up=1 FIR, 3x3 for 2x upsampling) is read with one vector load per pixel straight
+// from L1/L2 -- consecutive threads take consecutive channel vectors of the same patch, so every load and store of a warp
+// is one contiguous run along C.  No shared memory, no divisions / bounds checks per tap.
+template <typename T> struct V4;
+template <> struct V4<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) { const float4 t = __ldg(reinterpret_cast<const float4*>(p)); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+    static __device__ __forceinline__ void st(float* p, const float (&o)[4]) { __stcs(reinterpret_cast<float4*>(p), make_float4(o[0], o[1], o[2], o[3])); }
+};
+template <> struct V4<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float (&o)[4]) {
+        const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+    static __device__ __forceinline__ void st(__half* p, const float (&o)[4]) {
+        const __half2 a = __floats2half2_rn(o[0], o[1]), b = __floats2half2_rn(o[2], o[3]);
+        __stcs(reinterpret_cast<uint2*>(p), make_uint2(*reinterpret_cast<const unsigned*>(&a), *reinterpret_cast<const unsigned*>(&b)));
+    }
+};
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+__global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs p, int patches_x, int patches_y) {
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    float fk[FH][FW];
+#pragma unroll
+    for (int ky = 0; ky < FH; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < FW; ++kx) {
+            const int sy = p.flip ? ky : FH - 1 - ky, sx = p.flip ? kx : FW - 1 - kx;
+            fk[ky][kx] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
+        }
+    const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);
+    const unsigned cvn = (unsigned)(p.in_c >> 2);
+    const long long total = (long long)patches_x * patches_y * p.in_n * cvn;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r0 = i / cvn;
+        const int cv = (int)(i - r0 * cvn);
+        const int pxi = (int)(r0 % patches_x);
+        const long long r1 = r0 / patches_x;
+        const int pyi = (int)(r1 % patches_y);
+        const int n = (int)(r1 / patches_y);
+        const int ox0 = pxi * kPatch, oy0 = pyi * kPatch;
+        const int ix0 = ox0 * DX / UX - ax + AX::lo(), iy0 = oy0 * DY / UY - ay + AY::lo();
+        const T* xin = (const T*)p.x + n * p.isn + cv * 4;
+
+        float acc[kPatch][kPatch][4];
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a)
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+#pragma unroll
+        for (int r = 0; r < AY::kWin; ++r) {
+            const int gy = iy0 + r;
+            const bool rok = (unsigned)gy < (unsigned)p.in_h;
+            float win[AX::kWin][4];
+#pragma unroll
+            for (int q = 0; q < AX::kWin; ++q) {
+                const int gx = ix0 + q;
+                if (rok && (unsigned)gx < (unsigned)p.in_w) V4<T>::ld(xin + gy * p.ish + gx * p.isw, win[q]);
+                else { win[q][0] = 0.f; win[q][1] = 0.f; win[q][2] = 0.f; win[q][3] = 0.f; }
+            }
+#pragma unroll
+            for (int a = 0; a < kPatch; ++a) {
+#pragma unroll
+                for (int ty_ = 0; ty_ < AY::taps(a); ++ty_) {
+                    if (AY::off(a) - AY::lo() + ty_ != r) continue;              // folded at compile time
+                    const int ky = AY::k0(a) + ty_ * UY;
+#pragma unroll
+                    for (int b = 0; b < kPatch; ++b)
+#pragma unroll
+                        for (int tx_ = 0; tx_ < AX::taps(b); ++tx_) {
+                            const float w = fk[ky][AX::k0(b) + tx_ * UX];
+#pragma unroll
+                            for (int c = 0; c < 4; ++c) acc[a][b][c] = fmaf(w, win[AX::off(b) - AX::lo() + tx_][c], acc[a][b][c]);
+                        }
+                }
+            }
+        }
+        T* yout = (T*)p.y + n * p.osn + cv * 4;
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+            if (oy0 + a >= p.out_h) break;
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b)
+                if (ox0 + b < p.out_w) V4<T>::st(yout + (oy0 + a) * p.osh + (ox0 + b) * p.osw, acc[a][b]);
+        }
+    }
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+static int launch_cl_patch(const UpfirArgs& p, cudaStream_t st_) {
+    const int patches_x = ceil_div(p.out_w, kPatch), patches_y = ceil_div(p.out_h, kPatch);
+    const long long total = (long long)patches_x * patches_y * p.in_n * (p.in_c >> 2);
+    long long grid = ceil_div<long long>(total, 256);
+    const long long cap = (long long)sm_count() * 8;
+    if (grid > cap) grid = cap;
+    upfirdn2d_cl_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY><<<(unsigned)grid, 256, 0, st_>>>(p, patches_x, patches_y);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_cl_patch_kernel");
+    return IDE3D_OK;
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH>
+static int dispatch_phase_cl(const UpfirArgs& p, cudaStream_t s) {
+    const int phx = p.px0 - floor_div(p.px0, UX) * UX, phy = p.py0 - floor_div(p.py0, UY) * UY;
+    if constexpr (UX == 1 && UY == 1) return launch_cl_patch<T, UX, UY, DX, DY, FW, FH, 0, 0>(p, s);
+    if constexpr (UX == 2 && UY == 2) {
+        if (phx == 0 && phy == 0) return launch_cl_patch<T, 2, 2, DX, DY, FW, FH, 0, 0>(p, s);
+        if (phx == 1 && phy == 0) return launch_cl_patch<T, 2, 2, DX, DY, FW, FH, 1, 0>(p, s);
+        if (phx == 0 && phy == 1) return launch_cl_patch<T, 2, 2, DX, DY, FW, FH, 0, 1>(p, s);
+        return launch_cl_patch<T, 2, 2, DX, DY, FW, FH, 1, 1>(p, s);
+    }
+    IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: no channels_last phase table");
+}
+
+// ------------------------------------------------------------------------------------------
+// channels_last fallback (stride_c == 1): a thread owns one output pixel x 4 consecutive channels (one 16-byte vector for
 // fp32, 8 bytes for fp16), walks the live polyphase taps and reads the neighbouring input pixels straight from L1/L2
 // (adjacent outputs share them).  Any filter / factors; coalesced along C.
 template <typename T>
@@ -513,7 +635,23 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
         IDE3D_CASE(1, 1, 1, 1, 1, 12)
 #undef IDE3D_CASE
     }
-    if (p.isc == 1 && p.osc == 1 && (p.in_c & 3) == 0 && p.isw != 1) return launch_cl<T>(p, s);
+    if (p.isc == 1 && p.osc == 1 && (p.in_c & 3) == 0 && p.isw != 1) {
+        if constexpr (sizeof(T) <= 4) {
+            const long long vb = 4 * (long long)sizeof(T);                      // one channel vector: 16 bytes (fp32) / 8 bytes (fp16)
+            const bool aligned = ((reinterpret_cast<uintptr_t>(p.x) | reinterpret_cast<uintptr_t>(p.y)) % vb == 0) &&
+                                 ((p.isw | p.ish | p.isn | p.osw | p.osh | p.osn) % 4 == 0);
+            if (aligned) {
+#define IDE3D_CASE_CL(UX, UY, DX, DY, FW, FH)                                                           \
+    if (p.ux == UX && p.uy == UY && p.dx == DX && p.dy == DY && p.fw == FW && p.fh == FH)                \
+        return dispatch_phase_cl<T, UX, UY, DX, DY, FW, FH>(p, s);
+                IDE3D_CASE_CL(1, 1, 1, 1, 4, 4)
+                IDE3D_CASE_CL(2, 2, 1, 1, 4, 4)
+                IDE3D_CASE_CL(1, 1, 2, 2, 4, 4)
+#undef IDE3D_CASE_CL
+            }
+        }
+        return launch_cl<T>(p, s);
+    }
     return launch_generic<T>(p, s);
 }
 

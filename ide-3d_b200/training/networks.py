@@ -20,14 +20,23 @@ from ..torch_utils.ops import bias_act, conv2d_resample, fma, upfirdn2d
 
 FUSED_MODCONV_MIN_RES = 1 << 30      # block resolutions >= this use the grouped (weight-modulated) convolution
 
+# B200 layout choice: activations of every block are channels_last (NHWC) regardless of dtype.  The tf32 / fp16 tensor-core
+# convolutions cuDNN picks are NHWC kernels -- with NCHW tensors it brackets every convolution with nchwToNhwc / nhwcToNchw
+# passes (14 % of the step, profiles/r01_launches_bench_steady_state_final.txt) -- and the renderer gathers NHWC tri-planes
+# anyway.  The reference only does this for its fp16 layers (inversion/networks.py:746).  IDE3D_CHANNELS_LAST=0 restores
+# the reference's NCHW fp32 layout (same values).
+CHANNELS_LAST = os.environ.get('IDE3D_CHANNELS_LAST', '1') != '0'
+
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
     return x * (x.square().mean(dim=dim, keepdim=True) + eps).rsqrt()
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True):
-    """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I]."""
+                     flip_weight=True, fused_modconv=True, epilogue=None):
+    """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I].
+    epilogue (activation-scaled path only): dict(b, act, gain, clamp) -- the bias_act that always follows (:512, :707) is
+    then applied here, fused with the demodulation / noise pass (`bias_act.scaled_bias_act`)."""
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
     if x.dtype == torch.float16 and demodulate:      # keep fp16 in range (:78-81)
@@ -48,6 +57,8 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
         x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
         x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
                                             padding=padding, flip_weight=flip_weight)
+        if epilogue is not None:
+            return bias_act.scaled_bias_act(x, scale=dcoefs if demodulate else None, noise=noise, **epilogue)
         if demodulate and noise is not None:
             x = fma.fma(x, dcoefs.to(x.dtype).reshape(batch_size, -1, 1, 1), noise.to(x.dtype))
         elif demodulate:
@@ -64,6 +75,10 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     x = x.reshape(batch_size, -1, *x.shape[2:])
     if noise is not None:
         x = x.add_(noise)
+    if epilogue is not None:
+        b = epilogue['b']
+        return bias_act.bias_act(x, None if b is None else b.to(x.dtype), act=epilogue.get('act', 'linear'), gain=epilogue.get('gain'),
+                                 clamp=epilogue.get('clamp'))
     return x
 
 
@@ -173,11 +188,11 @@ class SynthesisLayer(torch.nn.Module):
             noise = torch.randn([x.shape[0], 1, self.up * x.shape[2], self.up * x.shape[3]], device=x.device) * self.noise_strength
         if self.use_noise and noise_mode == 'const':
             noise = self.noise_const * self.noise_strength
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
-                             resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv)
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
-        return bias_act.bias_act(x, self.bias.to(x.dtype), act=self.activation, gain=act_gain, clamp=act_clamp)
+        return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
+                                resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
+                                epilogue=dict(b=self.bias, act=self.activation, gain=act_gain, clamp=act_clamp))
 
 
 @persistence.persistent_class
@@ -195,8 +210,8 @@ class ToRGBLayer(torch.nn.Module):
 
     def forward(self, x, w, fused_modconv=True):
         styles = self.affine(w) * self.weight_gain
-        x = modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv)
-        return bias_act.bias_act(x, self.bias.to(x.dtype), clamp=self.conv_clamp)
+        return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv,
+                                epilogue=dict(b=self.bias, clamp=self.conv_clamp))
 
 
 @persistence.persistent_class
@@ -212,7 +227,7 @@ class SynthesisBlock(torch.nn.Module):
         self.resolution, self.img_channels, self.is_last = resolution, img_channels, is_last
         self.architecture = 'skip'
         self.use_fp16 = use_fp16
-        self.channels_last = use_fp16 and fp16_channels_last
+        self.channels_last = (use_fp16 and fp16_channels_last) or CHANNELS_LAST
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
         self.num_conv = 0
         self.num_torgb = 0
@@ -233,7 +248,7 @@ class SynthesisBlock(torch.nn.Module):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         w_iter = iter(ws.unbind(dim=1))
         dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
-        memory_format = torch.channels_last if self.channels_last and not force_fp32 else torch.contiguous_format
+        memory_format = torch.channels_last if self.channels_last and (CHANNELS_LAST or not force_fp32) else torch.contiguous_format
         if fused_modconv is None:
             fused_modconv = (not self.training) and (dtype == torch.float32 or int(ws.shape[0]) == 1)
             # Scaling activations instead of weights keeps the convolution a plain batched one (the grouped per-sample
@@ -242,8 +257,7 @@ class SynthesisBlock(torch.nn.Module):
             thr = int(os.environ.get('IDE3D_FUSED_MODCONV_MIN_RES', FUSED_MODCONV_MIN_RES))
             fused_modconv = fused_modconv and self.resolution >= thr
         if self.in_channels == 0:
-            x = self.const.to(dtype=dtype, memory_format=memory_format)
-            x = x.unsqueeze(0).repeat([ws.shape[0], 1, 1, 1])
+            x = self.const.to(dtype=dtype).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous(memory_format=memory_format)
             x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
         else:
             misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
@@ -256,6 +270,9 @@ class SynthesisBlock(torch.nn.Module):
         """Skip connection: upsample the running image with the FIR and add the new contribution."""
         if img is not None and img.shape[-1] * 2 == y.shape[-1]:
             img = upfirdn2d.upsample2d(img, self.resample_filter)
+        if CHANNELS_LAST and y.stride(1) == 1 and y.shape[1] % 4 == 0:      # keep NHWC (y may be a channel slice of the ToRGB output)
+            y = y.to(dtype=torch.float32)
+            return img.add_(y) if img is not None else y.contiguous(memory_format=torch.channels_last)
         y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
         return img.add_(y) if img is not None else y
 

@@ -25,6 +25,7 @@ import torch
 
 from .. import render
 from ..torch_utils import misc, persistence
+from . import networks
 from .networks import FullyConnectedLayer, MappingNetwork, SegSynthesisBlock, SynthesisBlock
 
 N_FEAT, N_SEG, N_OUT = 32, 19, 52
@@ -213,7 +214,9 @@ class SynthesisNetwork(torch.nn.Module):
         R = self.render_size
         feat, depth, _ = self.renderer(img_v, seg_v, cam2world, img_size=R, **kw)
         maps = feat.permute(0, 2, 1).reshape(n, N_OUT - 1, R, R)
-        feat_img, seg_raw = maps[:, :N_FEAT].contiguous(), maps[:, N_FEAT:]
+        # feat is [N, HW, 51]: already channels-last; keep that layout for the super-resolution blocks when they use it
+        sr_fmt = torch.channels_last if networks.CHANNELS_LAST else torch.contiguous_format
+        feat_img, seg_raw = maps[:, :N_FEAT].contiguous(memory_format=sr_fmt), maps[:, N_FEAT:]
         img = self.superres(feat_img, block_ws, **block_kwargs)
         out_size = (self.img_resolution, self.img_resolution)
         if return_dict:

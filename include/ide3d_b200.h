@@ -5,6 +5,7 @@
  * reference (citations are relative to the reference tree, MrTornado24/IDE-3D @ b2ee653):
  *
  *   ide3d_bias_act            torch_utils/ops/bias_act.cpp:32       (params: bias_act.h:12-31)
+ *   ide3d_modconv_epilogue    torch_utils/ops/fma.py:15 + bias_act.cpp:32 fused (extension; inversion/networks.py:104-105,512)
  *   ide3d_upfirdn2d           torch_utils/ops/upfirdn2d.cpp:16      (params: upfirdn2d.h:14-40)
  *   ide3d_filtered_lrelu      torch_utils/ops/filtered_lrelu.cpp:16 (params: filtered_lrelu.h:14-51)
  *   ide3d_filtered_lrelu_act  torch_utils/ops/filtered_lrelu.cpp:213 (params: filtered_lrelu.h:53-68)
@@ -67,6 +68,16 @@ uint64_t ide3d_launch_count(void);
 int ide3d_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy,
                    void* y, int dtype, int grad, int act, float alpha, float gain, float clamp,
                    int64_t size_x, int64_t size_b, int64_t step_b, ide3d_stream_t stream);
+
+/* Extension (no reference plugin): the tail of an activation-scaled modulated convolution in one pass,
+ *     y = bias_act(x * scale[n,c] + noise[(n),h,w], b[c], act, alpha, gain, clamp)
+ * i.e. fma.fma (inversion/networks.py:104-105; torch_utils/ops/fma.py:15) followed by bias_act (:512).
+ * x, y: [n, c, h*w] dense (channels_last = 0) or [n, h*w, c] dense (channels_last = 1), dtype as bias_act;
+ * scale [n*c], noise [noise_batch * h*w] (noise_batch = 1 or n), b [c]: same dtype as x, each may be NULL.
+ * Forward only.  IDE3D_UNSUPPORTED when the vector width does not divide h*w (NCHW) or c (channels_last). */
+int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y, int dtype,
+                           int act, float alpha, float gain, float clamp, int64_t n, int64_t c, int64_t hw,
+                           int64_t noise_batch, int channels_last, ide3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * upfirdn2d: pad -> zero-upsample -> FIR -> decimate.  Field meaning = upfirdn2d_kernel_params

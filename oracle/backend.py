@@ -70,6 +70,14 @@ def cpu_reference_ops():
     def ba(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
         return oops.bias_act(x, b, dim, act, alpha, gain, clamp)
 
+    def sba(x, scale=None, noise=None, b=None, act='linear', alpha=None, gain=None, clamp=None):
+        # the two reference ops the product fuses: fma (inversion/networks.py:104-105) then bias_act (:512)
+        if scale is not None:
+            x = x * scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1)
+        if noise is not None:
+            x = x + noise.to(x.dtype)
+        return oops.bias_act(x, None if b is None else b.to(x.dtype), 1, act, alpha, gain, clamp)
+
     def up(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
         return oops.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain)
 
@@ -77,10 +85,10 @@ def cpu_reference_ops():
         return oops.filtered_lrelu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter)
 
     R = p_tp.TriPlaneRenderer
-    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel)
-    p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu = ba, up, fl
+    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act)
+    p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, p_ba.scaled_bias_act = ba, up, fl, sba
     R.forward, R.sample_voxel = _renderer_forward, _renderer_sample_voxel
     try:
         yield
     finally:
-        p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel = saved
+        p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act = saved

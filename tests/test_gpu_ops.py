@@ -75,6 +75,57 @@ def test_bias_act_gradient_forms():
     assert_close(xg.grad, xr.grad, 1e-5); assert_close(bg.grad, br.grad, 1e-4)
 
 
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-6, 2e-6), (torch.float16, 4e-3, 1e-2), (torch.float64, 2e-7, 2e-7)])
+@pytest.mark.parametrize('cl', [False, True])
+@pytest.mark.parametrize('noise_kind,use_scale,use_bias', [('const', True, True), ('batch', True, True), (None, True, True),
+                                                           ('const', False, True), (None, False, False), ('batch', True, False)])
+def test_scaled_bias_act_is_fma_then_bias_act(dtype, atol, rtol, cl, noise_kind, use_scale, use_bias):
+    """Fused modconv tail == the two reference ops it replaces: fma(x, dcoefs, noise) (networks.py:104-105) -> bias_act (:512)."""
+    from ide3d_b200.torch_utils.ops import bias_act as ba
+    g = torch.Generator().manual_seed(7)
+    N, C, H, W = 3, 16, 12, 20
+    x = torch.randn(N, C, H, W, generator=g).to(dtype)
+    scale = (torch.rand(N, C, generator=g) + 0.5) if use_scale else None
+    noise = None if noise_kind is None else 0.3 * torch.randn((N if noise_kind == 'batch' else 1), 1, H, W, generator=g)
+    b = torch.randn(C, generator=g) if use_bias else None
+    t = x
+    if scale is not None:
+        t = t * scale.to(dtype).reshape(N, C, 1, 1)
+    if noise is not None:
+        t = t + noise.to(dtype)
+    want = oops.bias_act(t, None if b is None else b.to(dtype), 1, 'lrelu', None, 1.3, 0.8)
+    xd = x.to(DEV)
+    if cl:
+        xd = xd.contiguous(memory_format=torch.channels_last)
+    if noise_kind == 'const':
+        nd = noise.reshape(H, W).to(DEV)                     # the [H,W] noise_const * strength form of SynthesisLayer
+    else:
+        nd = None if noise is None else noise.to(DEV)
+    y = ba.scaled_bias_act(xd, None if scale is None else scale.to(DEV), nd, None if b is None else b.to(DEV), act='lrelu',
+                           gain=1.3, clamp=0.8)
+    assert y.dtype == dtype and y.shape == x.shape and y.stride() == xd.stride()
+    assert_close(y, want, atol, rtol)
+
+
+def test_scaled_bias_act_autograd_composes_reference_ops():
+    from ide3d_b200.torch_utils.ops import bias_act as ba
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 8, 8, 8, generator=g).to(DEV).requires_grad_(True)
+    scale = (torch.rand(2, 8, generator=g) + 0.5).to(DEV).requires_grad_(True)
+    noise = torch.randn(8, 8, generator=g).to(DEV)
+    b = torch.randn(8, generator=g).to(DEV).requires_grad_(True)
+    y = ba.scaled_bias_act(x, scale, noise, b, act='lrelu')
+    y.square().sum().backward()
+    with torch.no_grad():
+        y2 = ba.scaled_bias_act(x.detach(), scale.detach(), noise, b.detach(), act='lrelu')
+    assert_close(y, y2, 2e-6, 2e-6)
+    xr = x.detach().cpu().requires_grad_(True); sr = scale.detach().cpu().requires_grad_(True); br = b.detach().cpu().requires_grad_(True)
+    t = xr * sr.reshape(2, 8, 1, 1) + noise.cpu() + br.reshape(1, 8, 1, 1)
+    yr = torch.nn.functional.leaky_relu(t, 0.2) * math.sqrt(2)
+    yr.square().sum().backward()
+    assert_close(x.grad, xr.grad, 2e-5, 1e-5); assert_close(scale.grad, sr.grad, 2e-4, 1e-5); assert_close(b.grad, br.grad, 2e-4, 1e-5)
+
+
 # ---------------------------------------------------------------------------------------------- upfirdn2d
 UPFIR_CASES = {
     'up2_4x4': (2, 1, [2, 1, 2, 1], False, 4.0), 'down2_4x4': (1, 2, [1, 1, 1, 1], False, 1.0),
@@ -274,3 +325,27 @@ def test_upfirdn2d_channels_last_kernel_matches_contiguous_bitwise_shape():
         y = fn(xc, f.to(DEV))
         assert y.is_contiguous(memory_format=torch.channels_last)
         assert_close(y, ref(x, f), 1e-5)
+
+
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2)])
+@pytest.mark.parametrize('hw', [(64, 64), (37, 70), (5, 3)])
+def test_upfirdn2d_channels_last_patch_kernel_phases(dtype, atol, rtol, hw):
+    """channels_last + C % 4 == 0 + the 4x4 StyleGAN2 filter -> upfirdn2d_cl_patch_kernel; every padding phase, ragged
+    edges, negative padding (cropping) and sliced (non-dense) channel ranges."""
+    from ide3d_b200.torch_utils.ops import upfirdn2d as up
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(2, 12, *hw, generator=g).to(dtype)
+    f4 = oops.setup_filter([1, 3, 3, 1])
+    cases = [dict(up=2, padding=[2, 1, 2, 1], gain=4), dict(up=2, padding=[1, 2, 2, 1], gain=4), dict(up=2, padding=[3, 0, 1, 2]),
+             dict(up=2, padding=[2, 1, 1, 2]), dict(padding=[1, 1, 1, 1], gain=4), dict(padding=[2, 1, 0, 3]), dict(padding=[-1, 4, 3, -1]),
+             dict(down=2, padding=[1, 1, 1, 1]), dict(down=2, padding=[2, 0, 0, 2], flip_filter=True)]
+    xc = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    for kw in cases:
+        if min(hw) < 4 and kw.get('padding', [0])[0] < 0:
+            continue
+        ref = oops.upfirdn2d(x.double(), f4, **kw)
+        y = up.upfirdn2d(xc, f4.to(DEV), **kw)
+        assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+        assert_close(y, ref, atol, rtol, what=str(kw))
+        ys = up.upfirdn2d(xc[:, 4:12], f4.to(DEV), **kw)              # channel slice: stride_c == 1, pixel pitch 12
+        assert_close(ys, ref[:, 4:12], atol, rtol, what='slice ' + str(kw))
