@@ -60,10 +60,11 @@ def bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp):
     return y
 
 
-def modconv_epilogue(x, scale, noise, b, act, alpha, gain, clamp):
+def modconv_epilogue(x, scale, noise, b, act, alpha, gain, clamp, next_scale=None, only_next=False):
     """bias_act(x * scale[:, :, None, None] + noise, b) in one pass (extension, forward only).  x [N,C,H,W] dense NCHW or
-    channels_last; scale [N,C] | None; noise [H,W] / [1,1,H,W] / [N,1,H,W] | None; b [C] | None.  Returns None when the
-    kernel does not take the shape (caller composes the two reference ops instead)."""
+    channels_last; scale [N,C] | None; noise [H,W] / [1,1,H,W] / [N,1,H,W] | None; b [C] | None.  With next_scale [N,C] a
+    second tensor y * next_scale[:, :, None, None] is written in the same pass -> (y, y2), or y2 alone if only_next.
+    Returns None when the kernel does not take the shape (caller composes the reference ops instead)."""
     L.require_cuda(x)
     _req(x.ndim == 4, 'x must be rank 4')
     n, c, h, w = x.shape
@@ -83,17 +84,28 @@ def modconv_epilogue(x, scale, noise, b, act, alpha, gain, clamp):
     if _has(b):
         _req(b.ndim == 1 and b.shape[0] == c, 'b has wrong number of elements')
         b = b.to(dtype=x.dtype).contiguous()
-    y = torch.empty_like(x)
+    y = y2 = None
+    if _has(next_scale):
+        _req(next_scale.numel() == n * c, 'next_scale must have N*C elements')
+        next_scale = next_scale.to(dtype=x.dtype).reshape(n, c).contiguous()
+        y2 = torch.empty_like(x)
+    if not (only_next and y2 is not None):
+        y = torch.empty_like(x)
     rc = L.get_lib().ide3d_modconv_epilogue(L.ptr(x), L.ptr(scale) if _has(scale) else None, L.ptr(noise) if _has(noise) else None,
-                                            L.ptr(b) if _has(b) else None, L.ptr(y), L.dtype_code(x), int(act), float(alpha),
-                                            float(gain), float(clamp), n, c, h * w, noise_batch, int(cl), L.stream_ptr(x.device))
+                                            L.ptr(b) if _has(b) else None, L.ptr(y) if y is not None else None,
+                                            L.ptr(next_scale) if y2 is not None else None, L.ptr(y2) if y2 is not None else None,
+                                            L.dtype_code(x), int(act), float(alpha), float(gain), float(clamp), n, c, h * w,
+                                            noise_batch, int(cl), L.stream_ptr(x.device))
     if L.check(rc, allow_unsupported=True) == L.UNSUPPORTED:
         return None
-    return y
+    if y2 is None:
+        return y
+    return y2 if y is None else (y, y2)
 
 
 # ------------------------------------------------------------------------------------------- upfirdn2d
-def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain):
+def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, bias=None):
+    """add / bias (extension): y = upfirdn2d(x) + add + bias[c] in one pass; returns None if the kernel cannot fuse it."""
     L.require_cuda(x, f)
     _req(f.device == x.device, 'f must reside on the same device as x')
     _req(f.dtype == torch.float32, 'f must be float32')
@@ -114,6 +126,15 @@ def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
     p = L.UpfirParams(L.ptr(x), L.ptr(f), L.ptr(y), L.dtype_code(x), upx, upy, downx, downy, padx0, pady0,
                       1 if flip else 0, float(gain), w, h, c, n, xs[3], xs[2], xs[1], xs[0],
                       fw, fh, fs[1], fs[0], out_w, out_h, ys[3], ys[2], ys[1], ys[0])
+    if add is not None:
+        if tuple(add.shape) != (n, c, out_h, out_w) or add.dtype != x.dtype or add.stride(1) != 1 or not y.is_contiguous(memory_format=torch.channels_last) or y.is_contiguous():
+            return None
+        if bias is not None:
+            bias = bias.to(dtype=x.dtype).contiguous()
+        a = add.stride()
+        rc = L.get_lib().ide3d_upfirdn2d_add(C.byref(p), L.ptr(add), a[0], a[2], a[3], L.ptr(bias) if bias is not None else None,
+                                             L.stream_ptr(x.device))
+        return None if L.check(rc, allow_unsupported=True) == L.UNSUPPORTED else y
     L.check(L.get_lib().ide3d_upfirdn2d(C.byref(p), L.stream_ptr(x.device)))
     return y
 

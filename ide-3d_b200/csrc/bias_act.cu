@@ -309,7 +309,9 @@ namespace ide3d {
 
 struct EpiArgs {
     const void *x, *scale, *noise, *b;
-    void* y;
+    void* y;                              // may be NULL when only y2 is wanted
+    const void* scale2;                   // optional second output y2 = y * scale2[n,c]: the NEXT layer's style modulation
+    void* y2;
     float alpha, gain, clamp;
     long long n, c, hw;
     int noise_batch;                      // 1: one noise map for the whole batch, n: one per sample
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(256) modconv_epilogue_planar_kernel(const EpiA
         const long long smp = plane / p.c;
         const S d = p.scale ? to_acc<T>(((const T*)p.scale)[plane]) : (S)1;
         const S bias = p.b ? to_acc<T>(((const T*)p.b)[plane - smp * p.c]) : (S)0;
+        const S d2 = p.y2 ? to_acc<T>(((const T*)p.scale2)[plane]) : (S)1;
         const long long vbase = plane * plane_vecs;
         const long long nbase = (p.noise_batch == 1 ? 0 : smp) * plane_vecs;
         const long long v0 = chunk * (256 * UNROLL) + threadIdx.x;
@@ -368,7 +371,12 @@ __global__ void __launch_bounds__(256) modconv_epilogue_planar_kernel(const EpiA
                 const S t = p.noise ? vx[u][j] * d + vn[u][j] : vx[u][j] * d;
                 out[j] = eval<S, A>(t, bias, (S)0, (S)0, (S)1, 0, alpha, gain, clamp);
             }
-            store_vec((T*)p.y, vbase + vi, out);
+            if (p.y) store_vec((T*)p.y, vbase + vi, out);
+            if (p.y2) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) out[j] *= d2;
+                store_vec((T*)p.y2, vbase + vi, out);
+            }
         }
     }
 }
@@ -404,7 +412,14 @@ __global__ void __launch_bounds__(256) modconv_epilogue_cl_kernel(const EpiArgs 
                 if (p.noise) t = p.scale ? vx[u][j] * d[j] + nz : vx[u][j] + nz;
                 out[j] = eval<S, A>(t, p.b ? bb[j] : (S)0, (S)0, (S)0, (S)1, 0, alpha, gain, clamp);
             }
-            store_vec((T*)p.y, v, out);
+            if (p.y) store_vec((T*)p.y, v, out);
+            if (p.y2) {
+                S d2[N];
+                load_vec_keep<T>((const T*)p.scale2, smp * cv + c0, d2);
+#pragma unroll
+                for (int j = 0; j < N; ++j) out[j] *= d2[j];
+                store_vec((T*)p.y2, v, out);
+            }
         }
     }
 }
@@ -450,16 +465,18 @@ static int dispatch_epilogue(const EpiArgs& p, int act, int channels_last, cudaS
 
 }  // namespace ide3d
 
-extern "C" int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y, int dtype,
-                                      int act, float alpha, float gain, float clamp, int64_t n, int64_t c, int64_t hw,
-                                      int64_t noise_batch, int channels_last, ide3d_stream_t stream) {
+extern "C" int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y,
+                                      const void* scale2, void* y2, int dtype, int act, float alpha, float gain, float clamp,
+                                      int64_t n, int64_t c, int64_t hw, int64_t noise_batch, int channels_last,
+                                      ide3d_stream_t stream) {
     IDE3D_REQUIRE(n >= 0 && c >= 0 && hw >= 0, "modconv_epilogue: negative size");
     if (n * c * hw == 0) return IDE3D_OK;
-    IDE3D_REQUIRE(x && y, "modconv_epilogue: null x/y");
+    IDE3D_REQUIRE(x && (y || y2), "modconv_epilogue: null x / no output");
+    IDE3D_REQUIRE((y2 == nullptr) == (scale2 == nullptr), "modconv_epilogue: scale2 and y2 go together");
     IDE3D_REQUIRE(noise == nullptr || noise_batch == 1 || noise_batch == n, "modconv_epilogue: noise batch must be 1 or n");
-    const uintptr_t all = (uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)noise | (uintptr_t)b;
+    const uintptr_t all = (uintptr_t)x | (uintptr_t)y | (uintptr_t)scale | (uintptr_t)noise | (uintptr_t)b | (uintptr_t)scale2 | (uintptr_t)y2;
     IDE3D_REQUIRE((all & 15) == 0, "modconv_epilogue: tensors must be 16-byte aligned");
-    ide3d::EpiArgs p{x, scale, noise, b, y, alpha, gain, clamp, n, c, hw, (int)noise_batch};
+    ide3d::EpiArgs p{x, scale, noise, b, y, scale2, y2, alpha, gain, clamp, n, c, hw, (int)noise_batch};
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
         case IDE3D_F32: return ide3d::dispatch_epilogue<float>(p, act, channels_last, st);

@@ -80,6 +80,15 @@ struct TcArgs {
     int debug;                                     // IDE3D_TC_DEBUG: 1 = producers skip the gather, 2 = consumer skips the decoder (timing experiments only)
 };
 
+// log2(1 + 2^t): the hidden softplus in base-2 units (see the weight set-up).  ex2 of the clamped argument cannot overflow;
+// for t >= 24 the sum rounds to 2^t and lg2 returns t itself, and max(., t) keeps t beyond the clamp (the function is >= t).
+__device__ __forceinline__ float softplus2(float t) {
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(t, 126.f)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+    return fmaxf(l, t);
+}
+
 // write element (row, k) of a [rows x 64] bf16 swizzle-128B tile
 __device__ __forceinline__ void tile_store_bf16(unsigned char* tile, int row, int k, __nv_bfloat16 v) {
     *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, k >> 3) + (k & 7) * 2) = v;
@@ -152,8 +161,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         const int b = i >> 12, j = (i >> 6) & 63, k = i & 63;
         const TcBlock& B = P.blk[b];
         unsigned char* base = smem + kSmW + b * 4 * kWTileBytes;
-        const float v1 = (k >= B.k0 && k < B.k0 + B.kcount) ? B.w1[j * B.w1_ld + (k - B.k0)] : 0.f;   // W1[hidden j][input k]
-        const float v2 = (j >= B.out0 && j < B.out0 + B.outc) ? B.w2[(j - B.out0) * B.w2_ld + k] : 0.f; // W2[output j][hidden k]
+        // The hidden activation is evaluated in base 2: softplus(x) = ln2 * log2(1 + 2^(x*log2e)).  log2e is folded into W1 / b1
+        // and ln2 into W2 here, once, so the per-sample epilogue is add-bias, ex2, +1, lg2 (softplus2 below).
+        const float v1 = (k >= B.k0 && k < B.k0 + B.kcount) ? B.w1[j * B.w1_ld + (k - B.k0)] * 1.4426950408889634f : 0.f;   // W1[hidden j][input k]
+        const float v2 = (j >= B.out0 && j < B.out0 + B.outc) ? B.w2[(j - B.out0) * B.w2_ld + k] * 0.6931471805599453f : 0.f; // W2[output j][hidden k]
         __nv_bfloat16 hi, lo;
         tc::split_bf16(v1, hi, lo);
         tile_store_bf16(base, j, k, hi);
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         tile_store_bf16(base + 2 * kWTileBytes, j, k, hi);
         tile_store_bf16(base + 3 * kWTileBytes, j, k, lo);
     }
-    for (int i = tid; i < kTcMaxBlocks * 64; i += kTcThreads) b1s[i] = (i < P.nblocks * 64) ? P.blk[i >> 6].b1[i & 63] : 0.f;
+    for (int i = tid; i < kTcMaxBlocks * 64; i += kTcThreads) b1s[i] = (i < P.nblocks * 64) ? P.blk[i >> 6].b1[i & 63] * 1.4426950408889634f : 0.f;
     if (tid < 64) {
         float v = 0.f;
         for (int h = 0; h < a.dec.num_heads; ++h) {
@@ -313,8 +324,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
                         const float* bb = b1s + b * 64 + half * 32;
 #pragma unroll
                         for (int j = 0; j < 16; ++j) {
-                            const float h0 = softplus_mufu(v[2 * j] + bb[2 * j]);
-                            const float h1 = softplus_mufu(v[2 * j + 1] + bb[2 * j + 1]);
+                            const float h0 = softplus2(v[2 * j] + bb[2 * j]);
+                            const float h1 = softplus2(v[2 * j + 1] + bb[2 * j + 1]);
                             const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
                             const float2 back = __bfloat1622float2(hh);
                             const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);

@@ -32,6 +32,10 @@ struct UpfirArgs {
     long long fsw, fsh;
     int out_w, out_h;
     long long osw, osh, osc, osn;
+    // ide3d_upfirdn2d_add only (channels_last patch kernel): y = upfirdn2d(x) + add + bias[c]; add has stride_c == 1
+    const void* add = nullptr;
+    long long asw = 0, ash = 0, asn = 0;
+    const void* bias = nullptr;
 };
 
 template <typename T> struct AccT { using type = float; };
@@ -520,6 +524,23 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
             }
         }
         T* yout = (T*)p.y + n * p.osn + cv * 4;
+        if (p.add != nullptr) {                                  // skip-connection form: + new contribution (+ its bias)
+            const T* ain = (const T*)p.add + n * p.asn + cv * 4;
+            float bv[4] = {0.f, 0.f, 0.f, 0.f};
+            if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
+#pragma unroll
+            for (int a = 0; a < kPatch; ++a) {
+                if (oy0 + a >= p.out_h) break;
+#pragma unroll
+                for (int b = 0; b < kPatch; ++b)
+                    if (ox0 + b < p.out_w) {
+                        float av[4];
+                        V4<T>::ld(ain + (oy0 + a) * p.ash + (ox0 + b) * p.asw, av);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[a][b][c] += av[c] + bv[c];
+                    }
+            }
+        }
 #pragma unroll
         for (int a = 0; a < kPatch; ++a) {
             if (oy0 + a >= p.out_h) break;
@@ -620,7 +641,7 @@ static int launch_generic(const UpfirArgs& p, cudaStream_t s) {
 template <typename T>
 static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
     const bool wcontig = (p.isw == 1 && p.osw == 1);
-    if (wcontig && sizeof(T) <= 4) {
+    if (wcontig && sizeof(T) <= 4 && p.add == nullptr) {
 #define IDE3D_CASE(UX, UY, DX, DY, FW, FH)                                                              \
     if (p.ux == UX && p.uy == UY && p.dx == DX && p.dy == DY && p.fw == FW && p.fh == FH)                \
         return dispatch_phase<T, UX, UY, DX, DY, FW, FH>(p, s);
@@ -650,8 +671,9 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
 #undef IDE3D_CASE_CL
             }
         }
-        return launch_cl<T>(p, s);
+        if (p.add == nullptr) return launch_cl<T>(p, s);
     }
+    if (p.add != nullptr) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d_add: needs channels_last tensors, C %% 4 == 0 and a 4x4 filter with up/down in {1,2}");
     return launch_generic<T>(p, s);
 }
 
@@ -659,7 +681,8 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
 
 using namespace ide3d;
 
-extern "C" int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* q, ide3d_stream_t stream) {
+static int upfirdn2d_entry(const ide3d_upfirdn2d_params* q, const void* add, int64_t asn, int64_t ash, int64_t asw, const void* bias,
+                           ide3d_stream_t stream) {
     IDE3D_REQUIRE(q != nullptr, "upfirdn2d: null params");
     IDE3D_REQUIRE(q->x && q->f && q->y, "upfirdn2d: null tensor");
     IDE3D_REQUIRE(q->up_x >= 1 && q->up_y >= 1 && q->down_x >= 1 && q->down_y >= 1, "upsampling and downsampling factors must be at least 1");
@@ -675,6 +698,12 @@ extern "C" int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* q, ide3d_stream_t s
     p.fw = q->f_w; p.fh = q->f_h; p.fsw = q->f_stride_w; p.fsh = q->f_stride_h;
     p.out_w = q->out_w; p.out_h = q->out_h;
     p.osw = q->out_stride_w; p.osh = q->out_stride_h; p.osc = q->out_stride_c; p.osn = q->out_stride_n;
+    if (add != nullptr) {
+        const uintptr_t vb = (q->dtype == IDE3D_F16) ? 8 : 16;
+        IDE3D_REQUIRE(((uintptr_t)add % vb) == 0 && (bias == nullptr || ((uintptr_t)bias % vb) == 0) && (asn | ash | asw) % 4 == 0,
+                      "upfirdn2d_add: add / bias must be aligned to one 4-channel vector");
+        p.add = add; p.asn = asn; p.ash = ash; p.asw = asw; p.bias = bias;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     switch (q->dtype) {
         case IDE3D_F32: return dispatch_upfirdn2d<float>(p, s);
@@ -682,4 +711,14 @@ extern "C" int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* q, ide3d_stream_t s
         case IDE3D_F64: return dispatch_upfirdn2d<double>(p, s);
     }
     IDE3D_FAIL(IDE3D_INVALID, "upfirdn2d: unsupported dtype %d", q->dtype);
+}
+
+extern "C" int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* q, ide3d_stream_t stream) {
+    return upfirdn2d_entry(q, nullptr, 0, 0, 0, nullptr, stream);
+}
+
+extern "C" int ide3d_upfirdn2d_add(const ide3d_upfirdn2d_params* q, const void* add, int64_t add_stride_n, int64_t add_stride_h,
+                                   int64_t add_stride_w, const void* bias, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(add != nullptr, "upfirdn2d_add: null add tensor");
+    return upfirdn2d_entry(q, add, add_stride_n, add_stride_h, add_stride_w, bias, stream);
 }

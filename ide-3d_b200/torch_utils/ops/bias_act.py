@@ -105,27 +105,34 @@ def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, 
     return _plugin.bias_act(_layout(x), b, None, None, None, 0, dim, spec.cuda_idx, alpha, gain, clamp)
 
 
-def scaled_bias_act(x, scale=None, noise=None, b=None, act='linear', alpha=None, gain=None, clamp=None):
+def scaled_bias_act(x, scale=None, noise=None, b=None, act='linear', alpha=None, gain=None, clamp=None, next_scale=None,
+                    only_next=False):
     """Extension: ``bias_act(fma(x, scale[:, :, None, None], noise), b, act=...)`` -- the tail of an activation-scaled
     modulated convolution (inversion/networks.py:104-105 then :512) -- as ONE sm_100a pass when nothing needs a gradient;
     otherwise exactly that composition of the two reference ops (so autograd behaves as in the reference).
-    x [N,C,H,W]; scale [N,C] (demodulation coefficients) | None; noise broadcastable [.,1,H,W] | None; b [C] | None."""
+    x [N,C,H,W]; scale [N,C] (demodulation coefficients) | None; noise broadcastable [.,1,H,W] | None; b [C] | None.
+    next_scale [N,C]: additionally return ``y * next_scale[:, :, None, None]`` (the style modulation that opens the next
+    modulated convolution, :100) -> (y, y_next); with only_next just y_next."""
     from . import fma
     if x.device.type != 'cuda':
         raise RuntimeError('ide3d_b200.scaled_bias_act: x must be a CUDA tensor (no CPU path in this package)')
     _init()
     spec = activation_funcs[act]
-    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, scale, noise, b))
-    y = None
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, scale, noise, b, next_scale))
     if not needs_grad and x.ndim == 4:
-        y = _plugin.modconv_epilogue(_layout(x), scale, noise, b, spec.cuda_idx, float(alpha if alpha is not None else spec.def_alpha),
-                                     float(gain if gain is not None else spec.def_gain), float(clamp if clamp is not None else -1))
-    if y is None:
-        if scale is not None and noise is not None:
-            x = fma.fma(x, scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1), noise.to(x.dtype))
-        elif scale is not None:
-            x = x * scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1)
-        elif noise is not None:
-            x = x + noise.to(x.dtype)
-        y = bias_act(x, None if b is None else b.to(x.dtype), act=act, alpha=alpha, gain=gain, clamp=clamp)
-    return y
+        out = _plugin.modconv_epilogue(_layout(x), scale, noise, b, spec.cuda_idx, float(alpha if alpha is not None else spec.def_alpha),
+                                       float(gain if gain is not None else spec.def_gain), float(clamp if clamp is not None else -1),
+                                       next_scale=next_scale, only_next=only_next)
+        if out is not None:
+            return out
+    if scale is not None and noise is not None:
+        x = fma.fma(x, scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1), noise.to(x.dtype))
+    elif scale is not None:
+        x = x * scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1)
+    elif noise is not None:
+        x = x + noise.to(x.dtype)
+    y = bias_act(x, None if b is None else b.to(x.dtype), act=act, alpha=alpha, gain=gain, clamp=clamp)
+    if next_scale is None:
+        return y
+    y2 = y * next_scale.to(y.dtype).reshape(y.shape[0], -1, 1, 1)
+    return y2 if only_next else (y, y2)

@@ -147,6 +147,26 @@ def upsample2d(x, f, up=2, padding=0, flip_filter=False, gain=1, impl='cuda'):
     return upfirdn2d(x, f, up=up, padding=p, flip_filter=flip_filter, gain=gain * upx * upy, impl=impl)
 
 
+def upsample2d_add(x, f, y, b=None, up=2):
+    """Extension: ``upsample2d(x, f, up) + y + b[None, :, None, None]`` -- the skip-connection step of a 'skip' synthesis
+    block (inversion/networks.py:841-844, with the ToRGB bias of :707 folded in).  One pass when x is channels_last with
+    C % 4 == 0, f is the 2-D 4x4 filter, y has stride_c == 1 and nothing needs a gradient; otherwise the composition of the
+    reference ops (``y`` is then not modified)."""
+    if x.device.type != 'cuda':
+        raise RuntimeError('ide3d_b200.upsample2d_add: x must be a CUDA tensor (no CPU path in this package)')
+    _init()
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, y, b))
+    if not needs_grad and f is not None and f.ndim == 2 and y.dtype == x.dtype:
+        upx, upy = _parse_scaling(up)
+        fw, fh = _get_filter_size(f)
+        p = [(fw + upx - 1) // 2, (fw - upx) // 2, (fh + upy - 1) // 2, (fh - upy) // 2]
+        out = _plugin.upfirdn2d(x, f.to(x.device), upx, upy, 1, 1, p[0], p[1], p[2], p[3], False, float(upx * upy), add=y, bias=b)
+        if out is not None:
+            return out
+    out = upsample2d(x, f, up=up) + y
+    return out if b is None else out + b.to(out.dtype).reshape(1, -1, 1, 1)
+
+
 def downsample2d(x, f, down=2, padding=0, flip_filter=False, gain=1, impl='cuda'):
     """Downsample by an integer factor; output is 1/`down` of the input size (reference :352-387)."""
     downx, downy = _parse_scaling(down)

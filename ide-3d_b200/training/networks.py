@@ -26,6 +26,7 @@ FUSED_MODCONV_MIN_RES = 1 << 30      # block resolutions >= this use the grouped
 # anyway.  The reference only does this for its fp16 layers (inversion/networks.py:746).  IDE3D_CHANNELS_LAST=0 restores
 # the reference's NCHW fp32 layout (same values).
 CHANNELS_LAST = os.environ.get('IDE3D_CHANNELS_LAST', '1') != '0'
+CHAIN_MODULATION = True              # epilogues also write the next layer's `x * styles` (SynthesisBlock._features)
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -33,10 +34,12 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True, epilogue=None):
+                     flip_weight=True, fused_modconv=True, epilogue=None, premodulated=False):
     """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I].
     epilogue (activation-scaled path only): dict(b, act, gain, clamp) -- the bias_act that always follows (:512, :707) is
-    then applied here, fused with the demodulation / noise pass (`bias_act.scaled_bias_act`)."""
+    then applied here, fused with the demodulation / noise pass (`bias_act.scaled_bias_act`); optional keys next_scale /
+    only_next make that pass also emit `y * next_styles`, the input of the next activation-scaled convolution.
+    premodulated: x already carries `* styles` (written by the previous layer's epilogue)."""
     batch_size = x.shape[0]
     out_channels, in_channels, kh, kw = weight.shape
     if x.dtype == torch.float16 and demodulate:      # keep fp16 in range (:78-81)
@@ -53,8 +56,10 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
         # materialising the [N,O,I,k,k] modulated weight just to reduce it (same value up to fp32 summation order)
         dcoefs = (styles.square() @ weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
 
+    assert not (premodulated and (fused_modconv or (x.dtype == torch.float16 and demodulate)))
     if not fused_modconv:                           # scale activations instead of weights (:97-111)
-        x = x * styles.to(x.dtype).reshape(batch_size, -1, 1, 1)
+        if not premodulated:
+            x = bias_act.scaled_bias_act(x, scale=styles)       # x * styles[:, :, None, None]
         x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
                                             padding=padding, flip_weight=flip_weight)
         if epilogue is not None:
@@ -180,9 +185,13 @@ class SynthesisLayer(torch.nn.Module):
             self.noise_strength = torch.nn.Parameter(torch.zeros([]))
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
-    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1):
+    def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, styles=None, premodulated=False, next_styles=None,
+                only_next=False):
+        """styles / premodulated / next_styles / only_next: block-internal chaining of activation-scaled layers -- the
+        epilogue of this layer can already write `y * next_styles` for the layer that follows (see SynthesisBlock._features)."""
         assert noise_mode in ['random', 'const', 'none']
-        styles = self.affine(w)
+        if styles is None:
+            styles = self.affine(w)
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.up * x.shape[2], self.up * x.shape[3]], device=x.device) * self.noise_strength
@@ -190,9 +199,12 @@ class SynthesisLayer(torch.nn.Module):
             noise = self.noise_const * self.noise_strength
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
+        epilogue = dict(b=self.bias, act=self.activation, gain=act_gain, clamp=act_clamp)
+        if next_styles is not None:
+            epilogue.update(next_scale=next_styles, only_next=only_next)
         return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                 resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
-                                epilogue=dict(b=self.bias, act=self.activation, gain=act_gain, clamp=act_clamp))
+                                epilogue=epilogue, premodulated=premodulated)
 
 
 @persistence.persistent_class
@@ -208,10 +220,15 @@ class ToRGBLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
         self.weight_gain = 1 / np.sqrt(in_channels * (kernel_size ** 2))
 
-    def forward(self, x, w, fused_modconv=True):
-        styles = self.affine(w) * self.weight_gain
+    def styles(self, w):
+        return self.affine(w) * self.weight_gain
+
+    def forward(self, x, w, fused_modconv=True, styles=None, premodulated=False, raw=False):
+        """raw: return the convolution output WITHOUT the bias (the caller folds `self.bias` into the skip-connection pass)."""
+        if styles is None:
+            styles = self.styles(w)
         return modulated_conv2d(x=x, weight=self.weight, styles=styles, demodulate=False, fused_modconv=fused_modconv,
-                                epilogue=dict(b=self.bias, clamp=self.conv_clamp))
+                                epilogue=None if raw else dict(b=self.bias, clamp=self.conv_clamp), premodulated=premodulated)
 
 
 @persistence.persistent_class
@@ -256,15 +273,44 @@ class SynthesisBlock(torch.nn.Module):
             # rounding) and is faster below FUSED_MODCONV_MIN_RES on B200 (measured).
             thr = int(os.environ.get('IDE3D_FUSED_MODCONV_MIN_RES', FUSED_MODCONV_MIN_RES))
             fused_modconv = fused_modconv and self.resolution >= thr
+        # Inference in fp32 with activation scaling: every epilogue also writes the next layer's `x * styles`, so the
+        # separate modulation passes of conv1 and ToRGB disappear (conv0 -> x*s1 only; conv1 -> x and x*s_rgb).
+        chain = CHAIN_MODULATION and (not fused_modconv) and dtype == torch.float32 and not (torch.is_grad_enabled() and (
+            ws.requires_grad or any(p.requires_grad for p in self.parameters())))
+        rgb_in = None
         if self.in_channels == 0:
             x = self.const.to(dtype=dtype).unsqueeze(0).repeat([ws.shape[0], 1, 1, 1]).contiguous(memory_format=memory_format)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
+            w1 = next(w_iter)
         else:
             misc.assert_shape(x, [None, self.in_channels, self.resolution // 2, self.resolution // 2])
             x = x.to(dtype=dtype, memory_format=memory_format)
-            x = self.conv0(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-            x = self.conv1(x, next(w_iter), fused_modconv=fused_modconv, **layer_kwargs)
-        return x, next(w_iter), fused_modconv
+            w0, w1 = next(w_iter), next(w_iter)
+        w_rgb = next(w_iter)
+        if chain:
+            s1, s_rgb = self.conv1.affine(w1), self.torgb.styles(w_rgb)
+            pre = False
+            if self.in_channels != 0:
+                x = self.conv0(x, w0, fused_modconv=False, next_styles=s1, only_next=True, **layer_kwargs)
+                pre = True
+            x, x_rgb = self.conv1(x, w1, fused_modconv=False, styles=s1, premodulated=pre, next_styles=s_rgb, **layer_kwargs)
+            rgb_in = (x_rgb, s_rgb)
+        else:
+            if self.in_channels != 0:
+                x = self.conv0(x, w0, fused_modconv=fused_modconv, **layer_kwargs)
+            x = self.conv1(x, w1, fused_modconv=fused_modconv, **layer_kwargs)
+        return x, w_rgb, fused_modconv, rgb_in
+
+    def _torgb(self, x, w_rgb, fused_modconv, rgb_in, raw=False):
+        if rgb_in is not None:
+            return self.torgb(rgb_in[0], w_rgb, fused_modconv=False, styles=rgb_in[1], premodulated=True, raw=raw)
+        return self.torgb(x, w_rgb, fused_modconv=fused_modconv, raw=raw)
+
+    def _fuse_skip(self, rgb_in, *imgs):
+        """Can `upsample2d(img) + y + bias` run as one pass?  (chained fp32 inference, NHWC, no clamp, a running image at half
+        the resolution for every output group.)"""
+        return (rgb_in is not None and CHANNELS_LAST and self.torgb.conv_clamp is None and all(
+            i is not None and i.dtype == torch.float32 and i.shape[-1] * 2 == self.resolution and i.shape[1] % 4 == 0 and
+            i.stride(1) == 1 for i in imgs))
 
     def _accumulate(self, img, y):
         """Skip connection: upsample the running image with the FIR and add the new contribution."""
@@ -277,8 +323,11 @@ class SynthesisBlock(torch.nn.Module):
         return img.add_(y) if img is not None else y
 
     def forward(self, x, img, ws, force_fp32=False, fused_modconv=None, **layer_kwargs):
-        x, w_rgb, fused_modconv = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
-        img = self._accumulate(img, self.torgb(x, w_rgb, fused_modconv=fused_modconv))
+        x, w_rgb, fused_modconv, rgb_in = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
+        if self._fuse_skip(rgb_in, img):
+            y = self._torgb(x, w_rgb, fused_modconv, rgb_in, raw=True)
+            return x, upfirdn2d.upsample2d_add(img, self.resample_filter, y, self.torgb.bias)
+        img = self._accumulate(img, self._torgb(x, w_rgb, fused_modconv, rgb_in))
         return x, img
 
 
@@ -296,8 +345,13 @@ class SegSynthesisBlock(SynthesisBlock):
         self.img_channels, self.seg_channels = img_channels, seg_channels
 
     def forward(self, x, img, ws, condition_img=None, force_fp32=False, fused_modconv=None, **layer_kwargs):
-        x, w_shared, fused_modconv = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
-        y = self.torgb(x, w_shared, fused_modconv=fused_modconv)
+        x, w_shared, fused_modconv, rgb_in = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
+        if self._fuse_skip(rgb_in, img, condition_img):
+            y, b, ci = self._torgb(x, w_shared, fused_modconv, rgb_in, raw=True), self.torgb.bias, self.img_channels
+            img = upfirdn2d.upsample2d_add(img, self.resample_filter, y[:, :ci], b[:ci])
+            seg = upfirdn2d.upsample2d_add(condition_img, self.resample_filter, y[:, ci:], b[ci:])
+            return x, img, seg
+        y = self._torgb(x, w_shared, fused_modconv, rgb_in)
         img = self._accumulate(img, y[:, :self.img_channels])
         seg = self._accumulate(condition_img, y[:, self.img_channels:])
         return x, img, seg

@@ -191,9 +191,9 @@ class SynthesisNetwork(torch.nn.Module):
         return rgb
 
     def forward(self, ws, c=None, render_params=None, noise_mode='const', force_fp32=False, return_seg=False,
-                return_raw=False, return_dict=False, **render_overrides):
+                return_raw=False, return_dict=False, fused_modconv=None, **render_overrides):
         voxel_ws, block_ws = self.split_ws(ws)
-        block_kwargs = dict(noise_mode=noise_mode, force_fp32=force_fp32)
+        block_kwargs = dict(noise_mode=noise_mode, force_fp32=force_fp32, fused_modconv=fused_modconv)
         img_v, seg_v = self.backbone(voxel_ws, **block_kwargs)
 
         kw = dict(self.rendering_kwargs)

@@ -7,6 +7,7 @@
  *   ide3d_bias_act            torch_utils/ops/bias_act.cpp:32       (params: bias_act.h:12-31)
  *   ide3d_modconv_epilogue    torch_utils/ops/fma.py:15 + bias_act.cpp:32 fused (extension; inversion/networks.py:104-105,512)
  *   ide3d_upfirdn2d           torch_utils/ops/upfirdn2d.cpp:16      (params: upfirdn2d.h:14-40)
+ *   ide3d_upfirdn2d_add       upfirdn2d + the skip-connection add (extension; inversion/networks.py:841-844)
  *   ide3d_filtered_lrelu      torch_utils/ops/filtered_lrelu.cpp:16 (params: filtered_lrelu.h:14-51)
  *   ide3d_filtered_lrelu_act  torch_utils/ops/filtered_lrelu.cpp:213 (params: filtered_lrelu.h:53-68)
  *   ide3d_initial_rays        training/volumetric_rendering.py:77   get_initial_rays_trig
@@ -74,10 +75,13 @@ int ide3d_bias_act(const void* x, const void* b, const void* xref, const void* y
  * i.e. fma.fma (inversion/networks.py:104-105; torch_utils/ops/fma.py:15) followed by bias_act (:512).
  * x, y: [n, c, h*w] dense (channels_last = 0) or [n, h*w, c] dense (channels_last = 1), dtype as bias_act;
  * scale [n*c], noise [noise_batch * h*w] (noise_batch = 1 or n), b [c]: same dtype as x, each may be NULL.
+ * Optional second output y2 = y * scale2[n,c] (scale2 [n*c]; y2 like y): the style modulation `x * styles` that opens
+ * the NEXT modulated convolution (inversion/networks.py:100), written in the same pass; y may then be NULL.
  * Forward only.  IDE3D_UNSUPPORTED when the vector width does not divide h*w (NCHW) or c (channels_last). */
-int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y, int dtype,
-                           int act, float alpha, float gain, float clamp, int64_t n, int64_t c, int64_t hw,
-                           int64_t noise_batch, int channels_last, ide3d_stream_t stream);
+int ide3d_modconv_epilogue(const void* x, const void* scale, const void* noise, const void* b, void* y,
+                           const void* scale2, void* y2, int dtype, int act, float alpha, float gain, float clamp,
+                           int64_t n, int64_t c, int64_t hw, int64_t noise_batch, int channels_last,
+                           ide3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * upfirdn2d: pad -> zero-upsample -> FIR -> decimate.  Field meaning = upfirdn2d_kernel_params
@@ -99,6 +103,15 @@ typedef struct ide3d_upfirdn2d_params {
     int64_t out_stride_w, out_stride_h, out_stride_c, out_stride_n;
 } ide3d_upfirdn2d_params;
 int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* p, ide3d_stream_t stream);
+
+/* Extension (no reference plugin): the skip-connection step of a 'skip' synthesis block in one pass,
+ *     y = upfirdn2d(x, f, ...) + add + bias[c]
+ * i.e. upsample2d of the running image (inversion/networks.py:841) fused with the `img.add_(y)` that follows (:844) and
+ * with the ToRGB bias (:707).  add: same dtype, logical shape of y, element strides add_stride_{n,h,w}, channel stride 1
+ * (it may be a channel slice of a wider channels_last tensor); bias [c] or NULL.  Only the channels_last patch kernel
+ * implements it (x, y channels_last, C % 4 == 0, 4x4 filter, up/down in {1,2}); otherwise IDE3D_UNSUPPORTED. */
+int ide3d_upfirdn2d_add(const ide3d_upfirdn2d_params* p, const void* add, int64_t add_stride_n, int64_t add_stride_h,
+                        int64_t add_stride_w, const void* bias, ide3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * filtered_lrelu: bias -> up-FIR -> gain*lrelu*clamp (+ 2-bit sign tensor) -> down-FIR, fused.

@@ -70,13 +70,17 @@ def cpu_reference_ops():
     def ba(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
         return oops.bias_act(x, b, dim, act, alpha, gain, clamp)
 
-    def sba(x, scale=None, noise=None, b=None, act='linear', alpha=None, gain=None, clamp=None):
+    def sba(x, scale=None, noise=None, b=None, act='linear', alpha=None, gain=None, clamp=None, next_scale=None, only_next=False):
         # the two reference ops the product fuses: fma (inversion/networks.py:104-105) then bias_act (:512)
         if scale is not None:
             x = x * scale.to(x.dtype).reshape(x.shape[0], -1, 1, 1)
         if noise is not None:
             x = x + noise.to(x.dtype)
-        return oops.bias_act(x, None if b is None else b.to(x.dtype), 1, act, alpha, gain, clamp)
+        y = oops.bias_act(x, None if b is None else b.to(x.dtype), 1, act, alpha, gain, clamp)
+        if next_scale is None:
+            return y
+        y2 = y * next_scale.to(y.dtype).reshape(y.shape[0], -1, 1, 1)      # `x * styles` of the next layer (:100)
+        return y2 if only_next else (y, y2)
 
     def up(x, f, up=1, down=1, padding=0, flip_filter=False, gain=1, impl='cuda'):
         return oops.upfirdn2d(x, f, up=up, down=down, padding=padding, flip_filter=flip_filter, gain=gain)
@@ -84,11 +88,15 @@ def cpu_reference_ops():
     def fl(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=2 ** 0.5, slope=0.2, clamp=None, flip_filter=False, impl='cuda'):
         return oops.filtered_lrelu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter)
 
+    def upadd(x, f, y, b=None, up=2):
+        out = oops.upsample2d(x, f, up=up) + y                   # networks.py:841-844
+        return out if b is None else out + b.to(out.dtype).reshape(1, -1, 1, 1)
+
     R = p_tp.TriPlaneRenderer
-    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act)
-    p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, p_ba.scaled_bias_act = ba, up, fl, sba
+    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add)
+    p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, p_ba.scaled_bias_act, p_up.upsample2d_add = ba, up, fl, sba, upadd
     R.forward, R.sample_voxel = _renderer_forward, _renderer_sample_voxel
     try:
         yield
     finally:
-        p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act = saved
+        p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add = saved

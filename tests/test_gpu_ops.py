@@ -105,6 +105,14 @@ def test_scaled_bias_act_is_fma_then_bias_act(dtype, atol, rtol, cl, noise_kind,
                            gain=1.3, clamp=0.8)
     assert y.dtype == dtype and y.shape == x.shape and y.stride() == xd.stride()
     assert_close(y, want, atol, rtol)
+    # second output: the next layer's style modulation, written by the same pass
+    ns = torch.rand(N, C, generator=g) + 0.5
+    ya, yb = ba.scaled_bias_act(xd, None if scale is None else scale.to(DEV), nd, None if b is None else b.to(DEV), act='lrelu',
+                                gain=1.3, clamp=0.8, next_scale=ns.to(DEV))
+    yc = ba.scaled_bias_act(xd, None if scale is None else scale.to(DEV), nd, None if b is None else b.to(DEV), act='lrelu',
+                            gain=1.3, clamp=0.8, next_scale=ns.to(DEV), only_next=True)
+    assert torch.equal(ya, y) and torch.equal(yb, yc) and yb.stride() == xd.stride()
+    assert_close(yb, want.to(torch.float64) * ns.to(dtype).to(torch.float64).reshape(N, C, 1, 1), 2 * atol, 2 * rtol)
 
 
 def test_scaled_bias_act_autograd_composes_reference_ops():
@@ -349,3 +357,25 @@ def test_upfirdn2d_channels_last_patch_kernel_phases(dtype, atol, rtol, hw):
         assert_close(y, ref, atol, rtol, what=str(kw))
         ys = up.upfirdn2d(xc[:, 4:12], f4.to(DEV), **kw)              # channel slice: stride_c == 1, pixel pitch 12
         assert_close(ys, ref[:, 4:12], atol, rtol, what='slice ' + str(kw))
+
+
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2)])
+def test_upsample2d_add_is_upsample_then_add(dtype, atol, rtol):
+    """Skip-connection step in one pass == upsample2d (networks.py:841) + add (:844) + ToRGB bias (:707); `y` may be a channel
+    slice of a wider NHWC tensor.  NCHW inputs take the composed path and give the same values."""
+    from ide3d_b200.torch_utils.ops import upfirdn2d as up
+    g = torch.Generator().manual_seed(21)
+    img = torch.randn(2, 8, 9, 13, generator=g).to(dtype)
+    ywide = torch.randn(2, 20, 18, 26, generator=g).to(dtype)
+    b = torch.randn(8, generator=g).to(dtype)
+    f = oops.setup_filter([1, 3, 3, 1])
+    want = oops.upsample2d(img.double(), f) + ywide[:, 4:12].double() + b.double().reshape(1, -1, 1, 1)
+    yd = ywide.to(DEV).contiguous(memory_format=torch.channels_last)
+    keep = yd.clone()
+    out = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, 4:12], b.to(DEV))
+    assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(yd, keep)
+    assert_close(out, want, atol, rtol)
+    out2 = up.upsample2d_add(img.to(DEV), f.to(DEV), ywide[:, 4:12].to(DEV), b.to(DEV))          # NCHW: composed
+    assert_close(out2, want, atol, rtol)
+    out3 = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, 4:12], None)
+    assert_close(out3, want - b.double().reshape(1, -1, 1, 1), atol, rtol)

@@ -62,6 +62,27 @@ def test_synthesis_contract(G):
     assert torch.allclose(img_nolabel, img_label, atol=1e-5)
 
 
+def test_layout_and_chaining_switches_do_not_change_values(G):
+    """The B200 host-side choices -- NHWC activations, epilogues that pre-modulate the next layer, activation scaling
+    instead of weight modulation -- are re-orderings of the reference arithmetic (inversion/networks.py:97-129)."""
+    from ide3d_b200.training import networks as nw
+    z = torch.randn(2, G.z_dim, generator=torch.Generator().manual_seed(3))
+    c = torch.tensor(LABEL).repeat(2, 1)
+    outs = {}
+    saved = (nw.CHANNELS_LAST, nw.CHAIN_MODULATION)
+    try:
+        with cpu_reference_ops():
+            ws = G.mapping(z, c)
+            for cl, chain, fused in ((True, True, None), (False, True, None), (True, False, None), (False, False, True)):
+                nw.CHANNELS_LAST, nw.CHAIN_MODULATION = cl, chain
+                outs[(cl, chain, fused)] = G.synthesis(ws, c=c, noise_mode='const', num_steps=8, perturb=None, fused_modconv=fused)
+    finally:
+        nw.CHANNELS_LAST, nw.CHAIN_MODULATION = saved
+    ref = outs[(False, False, True)]                     # the reference's eval path: NCHW, grouped weight-modulated convs
+    for k, v in outs.items():
+        assert torch.allclose(v, ref, atol=2e-4, rtol=1e-4), (k, (v - ref).abs().max().item())
+
+
 def test_block_walk_of_extract_shapes(G):
     """The exact loop of extract_shapes.py:113-147 runs against the generator."""
     from ide3d_b200.torch_utils import misc
