@@ -32,6 +32,11 @@ class UpfirParams(C.Structure):
                 ('out_stride_w', C.c_int64), ('out_stride_h', C.c_int64), ('out_stride_c', C.c_int64), ('out_stride_n', C.c_int64)]
 
 
+class FirEpilogue(C.Structure):
+    _fields_ = [('scale', C.c_void_p), ('noise', C.c_void_p), ('b', C.c_void_p), ('scale2', C.c_void_p), ('y2', C.c_void_p),
+                ('act', C.c_int), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float), ('noise_batch', C.c_int64)]
+
+
 class FlreluParams(C.Structure):
     _fields_ = [('x', C.c_void_p), ('b', C.c_void_p), ('fu', C.c_void_p), ('fd', C.c_void_p), ('y', C.c_void_p),
                 ('s', C.c_void_p), ('dtype', C.c_int), ('up', C.c_int), ('down', C.c_int),
@@ -98,6 +103,7 @@ def get_lib():
     lib.ide3d_modconv_epilogue.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, i32, f32, f32, f32, i64, i64, i64, i64, i32, vp]
     lib.ide3d_upfirdn2d.argtypes = [C.POINTER(UpfirParams), vp]
     lib.ide3d_upfirdn2d_add.argtypes = [C.POINTER(UpfirParams), vp, i64, i64, i64, vp, vp]
+    lib.ide3d_upfirdn2d_epilogue.argtypes = [C.POINTER(UpfirParams), C.POINTER(FirEpilogue), vp]
     lib.ide3d_filtered_lrelu.argtypes = [C.POINTER(FlreluParams), vp]
     lib.ide3d_filtered_lrelu_act.argtypes = [C.POINTER(FlreluActParams), vp]
     lib.ide3d_raymarch_fwd.argtypes = [C.POINTER(RaymarchParams), vp]
@@ -123,7 +129,7 @@ def get_lib():
 def exported_symbols():
     """Names declared in include/ide3d_b200.h (used by the CPU test that checks the .so exports them)."""
     return ['ide3d_abi_version', 'ide3d_last_error', 'ide3d_launch_count', 'ide3d_bias_act', 'ide3d_modconv_epilogue',
-            'ide3d_upfirdn2d', 'ide3d_upfirdn2d_add',
+            'ide3d_upfirdn2d', 'ide3d_upfirdn2d_add', 'ide3d_upfirdn2d_epilogue',
             'ide3d_filtered_lrelu', 'ide3d_filtered_lrelu_act', 'ide3d_raymarch_fwd', 'ide3d_sample_voxel',
             'ide3d_sigma_grid', 'ide3d_planes_to_nhwc', 'ide3d_initial_rays', 'ide3d_transform_points',
             'ide3d_sample_triplane', 'ide3d_integrate', 'ide3d_sample_pdf']

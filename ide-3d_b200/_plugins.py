@@ -104,8 +104,11 @@ def modconv_epilogue(x, scale, noise, b, act, alpha, gain, clamp, next_scale=Non
 
 
 # ------------------------------------------------------------------------------------------- upfirdn2d
-def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, bias=None):
-    """add / bias (extension): y = upfirdn2d(x) + add + bias[c] in one pass; returns None if the kernel cannot fuse it."""
+def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain, add=None, bias=None, epilogue=None):
+    """Extensions (return None if the kernel cannot fuse them, so the caller composes the reference ops):
+    add / bias: y = upfirdn2d(x) + add + bias[c] in one pass;
+    epilogue = dict(scale, noise, b, act (1|3), alpha, gain, clamp, next_scale, only_next): the modulated-convolution tail applied
+    to the filter output, -> y | (y, y2) | y2 exactly like `modconv_epilogue`."""
     L.require_cuda(x, f)
     _req(f.device == x.device, 'f must reside on the same device as x')
     _req(f.dtype == torch.float32, 'f must be float32')
@@ -126,6 +129,36 @@ def upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, ga
     p = L.UpfirParams(L.ptr(x), L.ptr(f), L.ptr(y), L.dtype_code(x), upx, upy, downx, downy, padx0, pady0,
                       1 if flip else 0, float(gain), w, h, c, n, xs[3], xs[2], xs[1], xs[0],
                       fw, fh, fs[1], fs[0], out_w, out_h, ys[3], ys[2], ys[1], ys[0])
+    if epilogue is not None:
+        e = epilogue
+        if not (y.is_contiguous(memory_format=torch.channels_last) and not y.is_contiguous()) or e['act'] not in (1, 3) or x.dtype == torch.float64:
+            return None
+        def prep(t, numel):
+            if t is None:
+                return None
+            _req(t.numel() == numel, 'epilogue operand has the wrong number of elements')
+            return t.to(dtype=x.dtype).contiguous()
+        scale, b, scale2 = prep(e.get('scale'), n * c), prep(e.get('b'), c), prep(e.get('next_scale'), n * c)
+        noise = e.get('noise')
+        noise_batch = 1
+        if noise is not None:
+            _req(noise.numel() in (out_h * out_w, n * out_h * out_w), 'noise must be [H,W] or [N,1,H,W]')
+            noise_batch = noise.numel() // (out_h * out_w)
+            noise = noise.to(dtype=x.dtype).contiguous()
+        y2 = torch.empty_like(y) if scale2 is not None else None
+        want_y = not (e.get('only_next') and y2 is not None)
+        if not want_y:
+            p.y = None
+        ep = L.FirEpilogue(L.ptr(scale) if scale is not None else None, L.ptr(noise) if noise is not None else None,
+                           L.ptr(b) if b is not None else None, L.ptr(scale2) if scale2 is not None else None,
+                           L.ptr(y2) if y2 is not None else None, int(e['act']), float(e['alpha']), float(e['gain']),
+                           float(e['clamp']), noise_batch)
+        rc = L.get_lib().ide3d_upfirdn2d_epilogue(C.byref(p), C.byref(ep), L.stream_ptr(x.device))
+        if L.check(rc, allow_unsupported=True) == L.UNSUPPORTED:
+            return None
+        if y2 is None:
+            return y
+        return (y, y2) if want_y else y2
     if add is not None:
         if tuple(add.shape) != (n, c, out_h, out_w) or add.dtype != x.dtype or add.stride(1) != 1 or not y.is_contiguous(memory_format=torch.channels_last) or y.is_contiguous():
             return None

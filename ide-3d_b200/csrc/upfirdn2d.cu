@@ -36,6 +36,12 @@ struct UpfirArgs {
     const void* add = nullptr;
     long long asw = 0, ash = 0, asn = 0;
     const void* bias = nullptr;
+    // ide3d_upfirdn2d_epilogue only (channels_last patch kernel): the modulated-convolution tail applied to the FIR output
+    //   v = act(fir * scale[n,c] + noise[(n),oy,ox] + bias[c]) * gain, clamped;  y = v (if y != NULL);  y2 = v * scale2[n,c]
+    int epi = 0, act = 1, noise_batch = 1;
+    float alpha = 0.f, act_gain = 1.f, clamp = -1.f;
+    const void *scale = nullptr, *noise = nullptr, *scale2 = nullptr;
+    void* y2 = nullptr;
 };
 
 template <typename T> struct AccT { using type = float; };
@@ -461,7 +467,7 @@ template <> struct V4<__half> {
     }
 };
 
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi>
 __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs p, int patches_x, int patches_y) {
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
@@ -541,12 +547,47 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
                     }
             }
         }
+        if constexpr (kEpi) {
+            float dv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {1.f, 1.f, 1.f, 1.f};
+            if (p.scale != nullptr) V4<T>::ld((const T*)p.scale + (long long)n * p.in_c + cv * 4, dv);
+            if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
+            if (p.y2 != nullptr) V4<T>::ld((const T*)p.scale2 + (long long)n * p.in_c + cv * 4, d2);
+            const T* nz = (p.noise != nullptr) ? (const T*)p.noise + (p.noise_batch == 1 ? 0ll : (long long)n * p.out_h * p.out_w) : nullptr;
+            T* y2out = (p.y2 != nullptr) ? (T*)p.y2 + n * p.osn + cv * 4 : nullptr;
 #pragma unroll
-        for (int a = 0; a < kPatch; ++a) {
-            if (oy0 + a >= p.out_h) break;
+            for (int a = 0; a < kPatch; ++a) {
+                if (oy0 + a >= p.out_h) break;
 #pragma unroll
-            for (int b = 0; b < kPatch; ++b)
-                if (ox0 + b < p.out_w) V4<T>::st(yout + (oy0 + a) * p.osh + (ox0 + b) * p.osw, acc[a][b]);
+                for (int b = 0; b < kPatch; ++b) {
+                    if (ox0 + b >= p.out_w) continue;
+                    const float nv = nz ? ld<T>(nz + (long long)(oy0 + a) * p.out_w + (ox0 + b)) : 0.f;
+                    float v[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float t = nz ? fmaf(acc[a][b][c], dv[c], nv) : acc[a][b][c] * dv[c];
+                        t += bv[c];
+                        if (p.act == 3) t = (t > 0.f) ? t : t * p.alpha;
+                        t *= p.act_gain;
+                        if (p.clamp >= 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+                        v[c] = t;
+                    }
+                    const long long o = (long long)(oy0 + a) * p.osh + (long long)(ox0 + b) * p.osw;
+                    if (p.y != nullptr) V4<T>::st(yout + o, v);
+                    if (y2out != nullptr) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) v[c] *= d2[c];
+                        V4<T>::st(y2out + o, v);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int a = 0; a < kPatch; ++a) {
+                if (oy0 + a >= p.out_h) break;
+#pragma unroll
+                for (int b = 0; b < kPatch; ++b)
+                    if (ox0 + b < p.out_w) V4<T>::st(yout + (oy0 + a) * p.osh + (ox0 + b) * p.osw, acc[a][b]);
+            }
         }
     }
 }
@@ -558,7 +599,8 @@ static int launch_cl_patch(const UpfirArgs& p, cudaStream_t st_) {
     long long grid = ceil_div<long long>(total, 256);
     const long long cap = (long long)sm_count() * 8;
     if (grid > cap) grid = cap;
-    upfirdn2d_cl_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY><<<(unsigned)grid, 256, 0, st_>>>(p, patches_x, patches_y);
+    if (p.epi) upfirdn2d_cl_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, true><<<(unsigned)grid, 256, 0, st_>>>(p, patches_x, patches_y);
+    else upfirdn2d_cl_patch_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, false><<<(unsigned)grid, 256, 0, st_>>>(p, patches_x, patches_y);
     IDE3D_CHECK_LAUNCH("upfirdn2d_cl_patch_kernel");
     return IDE3D_OK;
 }
@@ -641,7 +683,7 @@ static int launch_generic(const UpfirArgs& p, cudaStream_t s) {
 template <typename T>
 static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
     const bool wcontig = (p.isw == 1 && p.osw == 1);
-    if (wcontig && sizeof(T) <= 4 && p.add == nullptr) {
+    if (wcontig && sizeof(T) <= 4 && p.add == nullptr && !p.epi) {
 #define IDE3D_CASE(UX, UY, DX, DY, FW, FH)                                                              \
     if (p.ux == UX && p.uy == UY && p.dx == DX && p.dy == DY && p.fw == FW && p.fh == FH)                \
         return dispatch_phase<T, UX, UY, DX, DY, FW, FH>(p, s);
@@ -671,9 +713,9 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
 #undef IDE3D_CASE_CL
             }
         }
-        if (p.add == nullptr) return launch_cl<T>(p, s);
+        if (p.add == nullptr && !p.epi) return launch_cl<T>(p, s);
     }
-    if (p.add != nullptr) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d_add: needs channels_last tensors, C %% 4 == 0 and a 4x4 filter with up/down in {1,2}");
+    if (p.add != nullptr || p.epi) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d_add/_epilogue: needs channels_last tensors, C %% 4 == 0 and a 4x4 filter with up/down in {1,2}");
     return launch_generic<T>(p, s);
 }
 
@@ -682,9 +724,9 @@ static int dispatch_upfirdn2d(const UpfirArgs& p, cudaStream_t s) {
 using namespace ide3d;
 
 static int upfirdn2d_entry(const ide3d_upfirdn2d_params* q, const void* add, int64_t asn, int64_t ash, int64_t asw, const void* bias,
-                           ide3d_stream_t stream) {
+                           ide3d_stream_t stream, const ide3d_fir_epilogue* e = nullptr) {
     IDE3D_REQUIRE(q != nullptr, "upfirdn2d: null params");
-    IDE3D_REQUIRE(q->x && q->f && q->y, "upfirdn2d: null tensor");
+    IDE3D_REQUIRE(q->x && q->f && (q->y || (e && e->y2)), "upfirdn2d: null tensor");
     IDE3D_REQUIRE(q->up_x >= 1 && q->up_y >= 1 && q->down_x >= 1 && q->down_y >= 1, "upsampling and downsampling factors must be at least 1");
     IDE3D_REQUIRE(q->f_w >= 1 && q->f_h >= 1, "f must be at least 1x1");
     IDE3D_REQUIRE(q->in_w > 0 && q->in_h > 0 && q->in_c > 0 && q->in_n > 0, "x is empty");
@@ -704,6 +746,17 @@ static int upfirdn2d_entry(const ide3d_upfirdn2d_params* q, const void* add, int
                       "upfirdn2d_add: add / bias must be aligned to one 4-channel vector");
         p.add = add; p.asn = asn; p.ash = ash; p.asw = asw; p.bias = bias;
     }
+    if (e != nullptr) {
+        const uintptr_t vb = (q->dtype == IDE3D_F16) ? 8 : 16;
+        const uintptr_t all = (uintptr_t)e->scale | (uintptr_t)e->b | (uintptr_t)e->scale2 | (uintptr_t)e->y2;
+        IDE3D_REQUIRE(all % vb == 0, "upfirdn2d_epilogue: scale / b / scale2 / y2 must be aligned to one 4-channel vector");
+        IDE3D_REQUIRE((e->y2 == nullptr) == (e->scale2 == nullptr), "upfirdn2d_epilogue: scale2 and y2 go together");
+        IDE3D_REQUIRE(e->noise == nullptr || e->noise_batch == 1 || e->noise_batch == q->in_n, "upfirdn2d_epilogue: noise batch must be 1 or n");
+        if (e->act != 1 && e->act != 3) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d_epilogue: only linear / lrelu are fused");
+        if (q->dtype == IDE3D_F64) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d_epilogue: fp64 is not fused");
+        p.epi = 1; p.act = e->act; p.alpha = e->alpha; p.act_gain = e->gain; p.clamp = e->clamp; p.noise_batch = (int)e->noise_batch;
+        p.scale = e->scale; p.noise = e->noise; p.bias = e->b; p.scale2 = e->scale2; p.y2 = e->y2;
+    }
     cudaStream_t s = (cudaStream_t)stream;
     switch (q->dtype) {
         case IDE3D_F32: return dispatch_upfirdn2d<float>(p, s);
@@ -721,4 +774,9 @@ extern "C" int ide3d_upfirdn2d_add(const ide3d_upfirdn2d_params* q, const void* 
                                    int64_t add_stride_w, const void* bias, ide3d_stream_t stream) {
     IDE3D_REQUIRE(add != nullptr, "upfirdn2d_add: null add tensor");
     return upfirdn2d_entry(q, add, add_stride_n, add_stride_h, add_stride_w, bias, stream);
+}
+
+extern "C" int ide3d_upfirdn2d_epilogue(const ide3d_upfirdn2d_params* q, const ide3d_fir_epilogue* e, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(e != nullptr, "upfirdn2d_epilogue: null epilogue");
+    return upfirdn2d_entry(q, nullptr, 0, 0, 0, nullptr, stream, e);
 }

@@ -18,8 +18,11 @@ def _conv(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True
     return op(x, w, stride=stride, padding=padding, groups=groups)
 
 
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, fir_epilogue=None):
+    """fir_epilogue (extension, up > 1 and down == 1 only): keyword arguments of `upfirdn2d.upfirdn2d_epilogue` -- the
+    modulated-convolution tail is then applied by the FIR pass that follows the transposed convolution."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
+    assert fir_epilogue is None or (up > 1 and down == 1 and not (int(w.shape[2]) == 1 and int(w.shape[3]) == 1))
     assert isinstance(w, torch.Tensor) and w.ndim == 4 and w.dtype == x.dtype
     assert f is None or (isinstance(f, torch.Tensor) and f.ndim in [1, 2] and f.dtype == torch.float32)
     assert isinstance(up, int) and up >= 1 and isinstance(down, int) and down >= 1 and isinstance(groups, int) and groups >= 1
@@ -55,6 +58,10 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         pxt = max(min(-px0, -px1), 0)
         pyt = max(min(-py0, -py1), 0)
         x = _conv(x, w, stride=up, padding=[pyt, pxt], groups=groups, transpose=True, flip_weight=(not flip_weight))
+        if fir_epilogue is not None:
+            assert down == 1
+            return upfirdn2d.upfirdn2d_epilogue(x, f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2,
+                                                flip_filter=flip_filter, **fir_epilogue)
         x = upfirdn2d.upfirdn2d(x=x, f=f, padding=[px0 + pxt, px1 + pxt, py0 + pyt, py1 + pyt], gain=up ** 2, flip_filter=flip_filter)
         if down > 1:
             x = upfirdn2d.upfirdn2d(x=x, f=f, down=down, flip_filter=flip_filter)

@@ -147,6 +147,31 @@ def upsample2d(x, f, up=2, padding=0, flip_filter=False, gain=1, impl='cuda'):
     return upfirdn2d(x, f, up=up, padding=p, flip_filter=flip_filter, gain=gain * upx * upy, impl=impl)
 
 
+def upfirdn2d_epilogue(x, f, padding=0, gain=1, flip_filter=False, scale=None, noise=None, b=None, act='linear', alpha=None,
+                       act_gain=None, clamp=None, next_scale=None, only_next=False):
+    """Extension: ``bias_act.scaled_bias_act(upfirdn2d(x, f, padding=padding, gain=gain), scale, noise, b, ...)`` -- what
+    follows the transposed convolution of an up=2 SynthesisLayer (conv2d_resample.py:125; inversion/networks.py:104-105, :512)
+    -- as one pass when x is channels_last (C % 4 == 0), f is the 4x4 filter and nothing needs a gradient; otherwise that
+    composition.  Returns y, (y, y_next) or y_next like `scaled_bias_act`."""
+    from . import bias_act
+    if x.device.type != 'cuda':
+        raise RuntimeError('ide3d_b200.upfirdn2d_epilogue: x must be a CUDA tensor (no CPU path in this package)')
+    _init()
+    spec = bias_act.activation_funcs[act]
+    needs_grad = torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (x, scale, noise, b, next_scale))
+    if not needs_grad and f is not None and f.ndim == 2 and spec.cuda_idx in (1, 3):
+        px0, px1, py0, py1 = _parse_padding(padding)
+        e = dict(scale=scale, noise=noise, b=b, act=spec.cuda_idx, alpha=float(alpha if alpha is not None else spec.def_alpha),
+                 gain=float(act_gain if act_gain is not None else spec.def_gain), clamp=float(clamp if clamp is not None else -1),
+                 next_scale=next_scale, only_next=only_next)
+        out = _plugin.upfirdn2d(x, f.to(x.device), 1, 1, 1, 1, px0, px1, py0, py1, bool(flip_filter), float(gain), epilogue=e)
+        if out is not None:
+            return out
+    y = upfirdn2d(x, f, padding=padding, gain=gain, flip_filter=flip_filter)
+    return bias_act.scaled_bias_act(y, scale=scale, noise=noise, b=b, act=act, alpha=alpha, gain=act_gain, clamp=clamp,
+                                    next_scale=next_scale, only_next=only_next)
+
+
 def upsample2d_add(x, f, y, b=None, up=2):
     """Extension: ``upsample2d(x, f, up) + y + b[None, :, None, None]`` -- the skip-connection step of a 'skip' synthesis
     block (inversion/networks.py:841-844, with the ToRGB bias of :707 folded in).  One pass when x is channels_last with

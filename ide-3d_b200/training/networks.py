@@ -60,6 +60,12 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     if not fused_modconv:                           # scale activations instead of weights (:97-111)
         if not premodulated:
             x = bias_act.scaled_bias_act(x, scale=styles)       # x * styles[:, :, None, None]
+        if epilogue is not None and up > 1 and down == 1 and kh > 1:      # the FIR after the transposed conv applies the tail
+            e = dict(epilogue)
+            e['act_gain'] = e.pop('gain', None)
+            e.update(scale=dcoefs if demodulate else None, noise=noise)
+            return conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
+                                                   padding=padding, flip_weight=flip_weight, fir_epilogue=e)
         x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
                                             padding=padding, flip_weight=flip_weight)
         if epilogue is not None:
@@ -244,7 +250,7 @@ class SynthesisBlock(torch.nn.Module):
         self.resolution, self.img_channels, self.is_last = resolution, img_channels, is_last
         self.architecture = 'skip'
         self.use_fp16 = use_fp16
-        self.channels_last = (use_fp16 and fp16_channels_last) or CHANNELS_LAST
+        self.channels_last = use_fp16 and fp16_channels_last
         self.register_buffer('resample_filter', upfirdn2d.setup_filter(resample_filter))
         self.num_conv = 0
         self.num_torgb = 0
@@ -253,19 +259,20 @@ class SynthesisBlock(torch.nn.Module):
         if in_channels != 0:
             self.conv0 = SynthesisLayer(in_channels, out_channels, w_dim=w_dim, resolution=resolution, up=2,
                                         resample_filter=resample_filter, conv_clamp=conv_clamp,
-                                        channels_last=self.channels_last, **layer_kwargs)
+                                        channels_last=self.channels_last or CHANNELS_LAST, **layer_kwargs)
             self.num_conv += 1
         self.conv1 = SynthesisLayer(out_channels, out_channels, w_dim=w_dim, resolution=resolution, conv_clamp=conv_clamp,
-                                    channels_last=self.channels_last, **layer_kwargs)
+                                    channels_last=self.channels_last or CHANNELS_LAST, **layer_kwargs)
         self.num_conv += 1
-        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp, channels_last=self.channels_last)
+        self.torgb = ToRGBLayer(out_channels, img_channels, w_dim=w_dim, conv_clamp=conv_clamp,
+                                channels_last=self.channels_last or CHANNELS_LAST)
         self.num_torgb += 1
 
     def _features(self, x, ws, force_fp32, fused_modconv, layer_kwargs):
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         w_iter = iter(ws.unbind(dim=1))
         dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
-        memory_format = torch.channels_last if self.channels_last and (CHANNELS_LAST or not force_fp32) else torch.contiguous_format
+        memory_format = torch.channels_last if CHANNELS_LAST or (self.channels_last and not force_fp32) else torch.contiguous_format
         if fused_modconv is None:
             fused_modconv = (not self.training) and (dtype == torch.float32 or int(ws.shape[0]) == 1)
             # Scaling activations instead of weights keeps the convolution a plain batched one (the grouped per-sample

@@ -8,6 +8,7 @@
  *   ide3d_modconv_epilogue    torch_utils/ops/fma.py:15 + bias_act.cpp:32 fused (extension; inversion/networks.py:104-105,512)
  *   ide3d_upfirdn2d           torch_utils/ops/upfirdn2d.cpp:16      (params: upfirdn2d.h:14-40)
  *   ide3d_upfirdn2d_add       upfirdn2d + the skip-connection add (extension; inversion/networks.py:841-844)
+ *   ide3d_upfirdn2d_epilogue  upfirdn2d + demodulation/noise/bias_act tail (extension; inversion/networks.py:104-105,512)
  *   ide3d_filtered_lrelu      torch_utils/ops/filtered_lrelu.cpp:16 (params: filtered_lrelu.h:14-51)
  *   ide3d_filtered_lrelu_act  torch_utils/ops/filtered_lrelu.cpp:213 (params: filtered_lrelu.h:53-68)
  *   ide3d_initial_rays        training/volumetric_rendering.py:77   get_initial_rays_trig
@@ -112,6 +113,23 @@ int ide3d_upfirdn2d(const ide3d_upfirdn2d_params* p, ide3d_stream_t stream);
  * implements it (x, y channels_last, C % 4 == 0, 4x4 filter, up/down in {1,2}); otherwise IDE3D_UNSUPPORTED. */
 int ide3d_upfirdn2d_add(const ide3d_upfirdn2d_params* p, const void* add, int64_t add_stride_n, int64_t add_stride_h,
                         int64_t add_stride_w, const void* bias, ide3d_stream_t stream);
+
+/* Extension (no reference plugin): upfirdn2d with the modulated-convolution tail applied to the filter output before it is
+ * stored -- the up=2 SynthesisLayer is conv_transpose2d -> FIR -> x*dcoefs + noise -> bias_act (inversion/networks.py:104-105,
+ * :512; conv2d_resample.py:112-126) and this runs everything after the transposed convolution in one pass:
+ *     v  = clamp(gain * act(fir * scale[n,c] + noise[(n),oy,ox] + b[c]))     act: 1 linear, 3 lrelu(alpha)
+ *     y  = v                      (params->y; may be NULL when only y2 is wanted)
+ *     y2 = v * scale2[n,c]        (optional: the next layer's style modulation, layout of y)
+ * scale, b, scale2: dtype of x, [n*c] / [c] / [n*c]; noise: dtype of x, [noise_batch, out_h, out_w] dense; any may be NULL.
+ * Same kernel restrictions as ide3d_upfirdn2d_add (channels_last, C % 4 == 0, 4x4 filter); otherwise IDE3D_UNSUPPORTED. */
+typedef struct ide3d_fir_epilogue {
+    const void *scale, *noise, *b, *scale2;
+    void* y2;
+    int act;
+    float alpha, gain, clamp;      /* clamp < 0: off */
+    int64_t noise_batch;           /* 1 or n */
+} ide3d_fir_epilogue;
+int ide3d_upfirdn2d_epilogue(const ide3d_upfirdn2d_params* p, const ide3d_fir_epilogue* e, ide3d_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * filtered_lrelu: bias -> up-FIR -> gain*lrelu*clamp (+ 2-bit sign tensor) -> down-FIR, fused.

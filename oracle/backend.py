@@ -62,10 +62,15 @@ def _renderer_sample_voxel(self, img_v, seg_v, points, sigma_only=False):
 
 
 @contextlib.contextmanager
-def cpu_reference_ops():
-    """Inside the context the product's op modules and renderer compute with the oracle on CPU tensors."""
+def cpu_reference_ops(reference_layout=True):
+    """Inside the context the product's op modules and renderer compute with the oracle on CPU tensors.
+    reference_layout: activations stay NCHW as in the reference's fp32 path (inversion/networks.py:746) -- the B200 build's
+    NHWC choice is a GPU layout decision and would only slow the CPU arm down; False keeps whatever the product is set to."""
     from ide3d_b200.torch_utils.ops import bias_act as p_ba, filtered_lrelu as p_fl, upfirdn2d as p_up
-    from ide3d_b200.training import triplane as p_tp
+    from ide3d_b200.training import networks as p_nw, triplane as p_tp
+    saved_layout = p_nw.CHANNELS_LAST
+    if reference_layout:
+        p_nw.CHANNELS_LAST = False
 
     def ba(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):
         return oops.bias_act(x, b, dim, act, alpha, gain, clamp)
@@ -88,15 +93,24 @@ def cpu_reference_ops():
     def fl(x, fu=None, fd=None, b=None, up=1, down=1, padding=0, gain=2 ** 0.5, slope=0.2, clamp=None, flip_filter=False, impl='cuda'):
         return oops.filtered_lrelu(x, fu, fd, b, up, down, padding, gain, slope, clamp, flip_filter)
 
+    def upepi(x, f, padding=0, gain=1, flip_filter=False, scale=None, noise=None, b=None, act='linear', alpha=None, act_gain=None,
+              clamp=None, next_scale=None, only_next=False):
+        y = oops.upfirdn2d(x, f, padding=padding, flip_filter=flip_filter, gain=gain)       # conv2d_resample.py:125
+        return sba(y, scale, noise, b, act, alpha, act_gain, clamp, next_scale, only_next)
+
     def upadd(x, f, y, b=None, up=2):
         out = oops.upsample2d(x, f, up=up) + y                   # networks.py:841-844
         return out if b is None else out + b.to(out.dtype).reshape(1, -1, 1, 1)
 
     R = p_tp.TriPlaneRenderer
-    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add)
+    saved = (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add,
+             p_up.upfirdn2d_epilogue)
     p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, p_ba.scaled_bias_act, p_up.upsample2d_add = ba, up, fl, sba, upadd
+    p_up.upfirdn2d_epilogue = upepi
     R.forward, R.sample_voxel = _renderer_forward, _renderer_sample_voxel
     try:
         yield
     finally:
-        p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add = saved
+        p_nw.CHANNELS_LAST = saved_layout
+        (p_ba.bias_act, p_up.upfirdn2d, p_fl.filtered_lrelu, R.forward, R.sample_voxel, p_ba.scaled_bias_act, p_up.upsample2d_add,
+         p_up.upfirdn2d_epilogue) = saved

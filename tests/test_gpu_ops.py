@@ -379,3 +379,38 @@ def test_upsample2d_add_is_upsample_then_add(dtype, atol, rtol):
     assert_close(out2, want, atol, rtol)
     out3 = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, 4:12], None)
     assert_close(out3, want - b.double().reshape(1, -1, 1, 1), atol, rtol)
+
+
+@pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 3e-5, 1e-5), (torch.float16, 3e-2, 2e-2)])
+@pytest.mark.parametrize('act,noise_kind', [('lrelu', 'const'), ('lrelu', 'batch'), ('linear', None), ('tanh', 'const')])
+def test_upfirdn2d_epilogue_is_fir_then_modconv_tail(dtype, atol, rtol, act, noise_kind):
+    """FIR + demodulation/noise/bias_act in one pass == conv2d_resample.py:125 followed by networks.py:104-105, :512.
+    ('tanh' is not fused by the kernel: the op composes upfirdn2d + scaled_bias_act and must give the same values.)"""
+    from ide3d_b200.torch_utils.ops import upfirdn2d as up
+    g = torch.Generator().manual_seed(31)
+    N, C, H, W = 2, 8, 19, 23                        # transposed-conv output of a 9x11 layer: (2r+1)
+    x = torch.randn(N, C, H, W, generator=g).to(dtype)
+    f = oops.setup_filter([1, 3, 3, 1])
+    pad = [1, 1, 1, 1]
+    scale = torch.rand(N, C, generator=g) + 0.5
+    ns = torch.rand(N, C, generator=g) + 0.5
+    b = torch.randn(C, generator=g)
+    fir = oops.upfirdn2d(x.double(), f, padding=pad, gain=4)
+    oh, ow = fir.shape[2:]
+    noise = None if noise_kind is None else 0.3 * torch.randn((N if noise_kind == 'batch' else 1), 1, oh, ow, generator=g)
+    t = fir * scale.to(dtype).double().reshape(N, C, 1, 1)
+    if noise is not None:
+        t = t + noise.to(dtype).double()
+    want = oops.bias_act(t, b.to(dtype).double(), 1, act, None, 1.2, 2.0)
+    xd = x.to(DEV).contiguous(memory_format=torch.channels_last)
+    nd = None if noise is None else (noise.reshape(oh, ow) if noise_kind == 'const' else noise).to(DEV)
+    kw = dict(padding=pad, gain=4, scale=scale.to(DEV), noise=nd, b=b.to(DEV), act=act, act_gain=1.2, clamp=2.0)
+    y = up.upfirdn2d_epilogue(xd, f.to(DEV), **kw)
+    assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    assert_close(y, want, atol, rtol)
+    ya, yb = up.upfirdn2d_epilogue(xd, f.to(DEV), next_scale=ns.to(DEV), **kw)
+    yc = up.upfirdn2d_epilogue(xd, f.to(DEV), next_scale=ns.to(DEV), only_next=True, **kw)
+    assert torch.equal(ya, y) and torch.equal(yb, yc)
+    assert_close(yb, want * ns.to(dtype).double().reshape(N, C, 1, 1), 2 * atol, 2 * rtol)
+    yn = up.upfirdn2d_epilogue(x.to(DEV), f.to(DEV), **kw)                       # NCHW: composed path
+    assert_close(yn, want, atol, rtol)

@@ -71,7 +71,7 @@ def test_layout_and_chaining_switches_do_not_change_values(G):
     outs = {}
     saved = (nw.CHANNELS_LAST, nw.CHAIN_MODULATION)
     try:
-        with cpu_reference_ops():
+        with cpu_reference_ops(reference_layout=False):
             ws = G.mapping(z, c)
             for cl, chain, fused in ((True, True, None), (False, True, None), (True, False, None), (False, False, True)):
                 nw.CHANNELS_LAST, nw.CHAIN_MODULATION = cl, chain
