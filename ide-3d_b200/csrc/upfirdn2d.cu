@@ -467,11 +467,106 @@ template <> struct V4<__half> {
     }
 };
 
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi>
-__global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs p, int patches_x, int patches_y) {
+// One 4x4 output patch x 4 channels: accumulate from a window supplied by `load(r, q, out[4])` (global memory with bounds
+// checks, or a TMA-staged shared-memory tile), then the optional skip-add / modconv tail, then the stores.
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi, typename LoadFn>
+__device__ __forceinline__ void cl_patch_body(const UpfirArgs& p, const float (&fk)[FH][FW], int n, int cv, int ox0, int oy0, LoadFn load) {
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
-    float fk[FH][FW];
+    float acc[kPatch][kPatch][4];
+#pragma unroll
+    for (int a = 0; a < kPatch; ++a)
+#pragma unroll
+        for (int b = 0; b < kPatch; ++b)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+
+#pragma unroll
+    for (int r = 0; r < AY::kWin; ++r) {
+        float win[AX::kWin][4];
+#pragma unroll
+        for (int q = 0; q < AX::kWin; ++q) load(r, q, win[q]);
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+#pragma unroll
+            for (int ty_ = 0; ty_ < AY::taps(a); ++ty_) {
+                if (AY::off(a) - AY::lo() + ty_ != r) continue;              // folded at compile time
+                const int ky = AY::k0(a) + ty_ * UY;
+#pragma unroll
+                for (int b = 0; b < kPatch; ++b)
+#pragma unroll
+                    for (int tx_ = 0; tx_ < AX::taps(b); ++tx_) {
+                        const float w = fk[ky][AX::k0(b) + tx_ * UX];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) acc[a][b][c] = fmaf(w, win[AX::off(b) - AX::lo() + tx_][c], acc[a][b][c]);
+                    }
+            }
+        }
+    }
+    T* yout = (T*)p.y + n * p.osn + cv * 4;
+    if (p.add != nullptr) {                                  // skip-connection form: + new contribution (+ its bias)
+        const T* ain = (const T*)p.add + n * p.asn + cv * 4;
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+            if (oy0 + a >= p.out_h) break;
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b)
+                if (ox0 + b < p.out_w) {
+                    float av[4];
+                    V4<T>::ld(ain + (oy0 + a) * p.ash + (ox0 + b) * p.asw, av);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][b][c] += av[c] + bv[c];
+                }
+        }
+    }
+    if constexpr (kEpi) {
+        float dv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {1.f, 1.f, 1.f, 1.f};
+        if (p.scale != nullptr) V4<T>::ld((const T*)p.scale + (long long)n * p.in_c + cv * 4, dv);
+        if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
+        if (p.y2 != nullptr) V4<T>::ld((const T*)p.scale2 + (long long)n * p.in_c + cv * 4, d2);
+        const T* nz = (p.noise != nullptr) ? (const T*)p.noise + (p.noise_batch == 1 ? 0ll : (long long)n * p.out_h * p.out_w) : nullptr;
+        T* y2out = (p.y2 != nullptr) ? (T*)p.y2 + n * p.osn + cv * 4 : nullptr;
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+            if (oy0 + a >= p.out_h) break;
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b) {
+                if (ox0 + b >= p.out_w) continue;
+                const float nv = nz ? ld<T>(nz + (long long)(oy0 + a) * p.out_w + (ox0 + b)) : 0.f;
+                float v[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float t = nz ? fmaf(acc[a][b][c], dv[c], nv) : acc[a][b][c] * dv[c];
+                    t += bv[c];
+                    if (p.act == 3) t = (t > 0.f) ? t : t * p.alpha;
+                    t *= p.act_gain;
+                    if (p.clamp >= 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
+                    v[c] = t;
+                }
+                const long long o = (long long)(oy0 + a) * p.osh + (long long)(ox0 + b) * p.osw;
+                if (p.y != nullptr) V4<T>::st(yout + o, v);
+                if (y2out != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) v[c] *= d2[c];
+                    V4<T>::st(y2out + o, v);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+            if (oy0 + a >= p.out_h) break;
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b)
+                if (ox0 + b < p.out_w) V4<T>::st(yout + (oy0 + a) * p.osh + (ox0 + b) * p.osw, acc[a][b]);
+        }
+    }
+}
+
+template <int FW, int FH>
+__device__ __forceinline__ void load_filter(const UpfirArgs& p, float (&fk)[FH][FW]) {
 #pragma unroll
     for (int ky = 0; ky < FH; ++ky)
 #pragma unroll
@@ -479,6 +574,14 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
             const int sy = p.flip ? ky : FH - 1 - ky, sx = p.flip ? kx : FW - 1 - kx;
             fk[ky][kx] = p.f[sy * p.fsh + sx * p.fsw] * p.gain;
         }
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi>
+__global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs p, int patches_x, int patches_y) {
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    float fk[FH][FW];
+    load_filter<FW, FH>(p, fk);
     const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);
     const unsigned cvn = (unsigned)(p.in_c >> 2);
     const long long total = (long long)patches_x * patches_y * p.in_n * cvn;
@@ -492,108 +595,142 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
         const int ox0 = pxi * kPatch, oy0 = pyi * kPatch;
         const int ix0 = ox0 * DX / UX - ax + AX::lo(), iy0 = oy0 * DY / UY - ay + AY::lo();
         const T* xin = (const T*)p.x + n * p.isn + cv * 4;
+        cl_patch_body<T, UX, UY, DX, DY, FW, FH, PHX, PHY, kEpi>(p, fk, n, cv, ox0, oy0, [&](int r, int q, float (&w)[4]) {
+            const int gy = iy0 + r, gx = ix0 + q;
+            if ((unsigned)gy < (unsigned)p.in_h && (unsigned)gx < (unsigned)p.in_w) V4<T>::ld(xin + gy * p.ish + gx * p.isw, w);
+            else { w[0] = 0.f; w[1] = 0.f; w[2] = 0.f; w[3] = 0.f; }
+        });
+    }
+}
 
-        float acc[kPatch][kPatch][4];
-#pragma unroll
-        for (int a = 0; a < kPatch; ++a)
-#pragma unroll
-            for (int b = 0; b < kPatch; ++b)
-#pragma unroll
-                for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+// TMA-staged channels_last flavour (C % 32 == 0): a block owns a 32 x 16 pixel output tile x 32 channels; the input box
+// (channels x columns x rows of a 4-D tensor map, zero-filled outside the image by the TMA unit) arrives with ONE
+// cp.async.bulk.tensor.4d per tile, double-buffered against the FIR of the previous tile.  Shared-memory pixels are 128-byte
+// (fp32) runs of 32 channels, so the 8 lanes that share a patch read one contiguous line per window element.
+constexpr int kClTileW = 32, kClTileH = 16, kClCB = 32;
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+struct ClTmaGeom {
+    using AX = Axis<UX, DX, FW, PHX>;
+    using AY = Axis<UY, DY, FH, PHY>;
+    static constexpr int BW = (kClTileW / kPatch - 1) * AX::kStep + AX::kWin;
+    static constexpr int BH = (kClTileH / kPatch - 1) * AY::kStep + AY::kWin;
+    static constexpr int kTileBytes = ((BW * BH * kClCB * (int)sizeof(T) + 127) / 128) * 128;
+    static constexpr int kSmem = 2 * kTileBytes + 128 + 128;
+};
+__device__ __forceinline__ void tma_load_tile4(void* dst, const CUtensorMap* map, unsigned long long* bar, int c, int x, int y, int n, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(smem_addr(dst)), "l"(map), "r"(smem_addr(bar)), "r"(c), "r"(x), "r"(y), "r"(n) : "memory");
+}
+template <typename T> struct V4s;
+template <> struct V4s<float> {
+    static __device__ __forceinline__ void ld(const float* p, float (&o)[4]) { const float4 t = *reinterpret_cast<const float4*>(p); o[0] = t.x; o[1] = t.y; o[2] = t.z; o[3] = t.w; }
+};
+template <> struct V4s<__half> {
+    static __device__ __forceinline__ void ld(const __half* p, float (&o)[4]) {
+        const uint2 t = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+    }
+};
 
-#pragma unroll
-        for (int r = 0; r < AY::kWin; ++r) {
-            const int gy = iy0 + r;
-            const bool rok = (unsigned)gy < (unsigned)p.in_h;
-            float win[AX::kWin][4];
-#pragma unroll
-            for (int q = 0; q < AX::kWin; ++q) {
-                const int gx = ix0 + q;
-                if (rok && (unsigned)gx < (unsigned)p.in_w) V4<T>::ld(xin + gy * p.ish + gx * p.isw, win[q]);
-                else { win[q][0] = 0.f; win[q][1] = 0.f; win[q][2] = 0.f; win[q][3] = 0.f; }
-            }
-#pragma unroll
-            for (int a = 0; a < kPatch; ++a) {
-#pragma unroll
-                for (int ty_ = 0; ty_ < AY::taps(a); ++ty_) {
-                    if (AY::off(a) - AY::lo() + ty_ != r) continue;              // folded at compile time
-                    const int ky = AY::k0(a) + ty_ * UY;
-#pragma unroll
-                    for (int b = 0; b < kPatch; ++b)
-#pragma unroll
-                        for (int tx_ = 0; tx_ < AX::taps(b); ++tx_) {
-                            const float w = fk[ky][AX::k0(b) + tx_ * UX];
-#pragma unroll
-                            for (int c = 0; c < 4; ++c) acc[a][b][c] = fmaf(w, win[AX::off(b) - AX::lo() + tx_][c], acc[a][b][c]);
-                        }
-                }
-            }
-        }
-        T* yout = (T*)p.y + n * p.osn + cv * 4;
-        if (p.add != nullptr) {                                  // skip-connection form: + new contribution (+ its bias)
-            const T* ain = (const T*)p.add + n * p.asn + cv * 4;
-            float bv[4] = {0.f, 0.f, 0.f, 0.f};
-            if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
-#pragma unroll
-            for (int a = 0; a < kPatch; ++a) {
-                if (oy0 + a >= p.out_h) break;
-#pragma unroll
-                for (int b = 0; b < kPatch; ++b)
-                    if (ox0 + b < p.out_w) {
-                        float av[4];
-                        V4<T>::ld(ain + (oy0 + a) * p.ash + (ox0 + b) * p.asw, av);
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) acc[a][b][c] += av[c] + bv[c];
-                    }
-            }
-        }
-        if constexpr (kEpi) {
-            float dv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {1.f, 1.f, 1.f, 1.f};
-            if (p.scale != nullptr) V4<T>::ld((const T*)p.scale + (long long)n * p.in_c + cv * 4, dv);
-            if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
-            if (p.y2 != nullptr) V4<T>::ld((const T*)p.scale2 + (long long)n * p.in_c + cv * 4, d2);
-            const T* nz = (p.noise != nullptr) ? (const T*)p.noise + (p.noise_batch == 1 ? 0ll : (long long)n * p.out_h * p.out_w) : nullptr;
-            T* y2out = (p.y2 != nullptr) ? (T*)p.y2 + n * p.osn + cv * 4 : nullptr;
-#pragma unroll
-            for (int a = 0; a < kPatch; ++a) {
-                if (oy0 + a >= p.out_h) break;
-#pragma unroll
-                for (int b = 0; b < kPatch; ++b) {
-                    if (ox0 + b >= p.out_w) continue;
-                    const float nv = nz ? ld<T>(nz + (long long)(oy0 + a) * p.out_w + (ox0 + b)) : 0.f;
-                    float v[4];
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) {
-                        float t = nz ? fmaf(acc[a][b][c], dv[c], nv) : acc[a][b][c] * dv[c];
-                        t += bv[c];
-                        if (p.act == 3) t = (t > 0.f) ? t : t * p.alpha;
-                        t *= p.act_gain;
-                        if (p.clamp >= 0.f) t = fminf(fmaxf(t, -p.clamp), p.clamp);
-                        v[c] = t;
-                    }
-                    const long long o = (long long)(oy0 + a) * p.osh + (long long)(ox0 + b) * p.osw;
-                    if (p.y != nullptr) V4<T>::st(yout + o, v);
-                    if (y2out != nullptr) {
-#pragma unroll
-                        for (int c = 0; c < 4; ++c) v[c] *= d2[c];
-                        V4<T>::st(y2out + o, v);
-                    }
-                }
-            }
-        } else {
-#pragma unroll
-            for (int a = 0; a < kPatch; ++a) {
-                if (oy0 + a >= p.out_h) break;
-#pragma unroll
-                for (int b = 0; b < kPatch; ++b)
-                    if (ox0 + b < p.out_w) V4<T>::st(yout + (oy0 + a) * p.osh + (ox0 + b) * p.osw, acc[a][b]);
-            }
-        }
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi>
+__global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p, int tiles_x, int tiles_y, int cblocks,
+                                                               const __grid_constant__ CUtensorMap tmap) {
+    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    using AX = typename GM::AX;
+    using AY = typename GM::AY;
+    extern __shared__ unsigned char tma_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw) + 127) & ~(uintptr_t)127);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + 2 * GM::kTileBytes);
+    float fk[FH][FW];
+    load_filter<FW, FH>(p, fk);
+    const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);
+    const long long total = (long long)tiles_x * tiles_y * cblocks * p.in_n;
+    constexpr unsigned kBytes = GM::BW * GM::BH * kClCB * sizeof(T);
+
+    // tile index -> (n, channel block, tile y, tile x); x fastest so that concurrently resident blocks share halo rows in L2
+    auto coords = [&](long long t, int& n, int& cb, int& ox_t, int& oy_t) {
+        const int tx = (int)(t % tiles_x); t /= tiles_x;
+        const int ty = (int)(t % tiles_y); t /= tiles_y;
+        cb = (int)(t % cblocks); n = (int)(t / cblocks);
+        ox_t = tx * kClTileW; oy_t = ty * kClTileH;
+    };
+    auto issue = [&](long long t, int buf) {
+        int n, cb, ox_t, oy_t;
+        coords(t, n, cb, ox_t, oy_t);
+        tma_load_tile4(base + buf * GM::kTileBytes, &tmap, &bars[buf], cb * kClCB, ox_t * DX / UX - ax + AX::lo(),
+                       oy_t * DY / UY - ay + AY::lo(), n, kBytes);
+    };
+    if (threadIdx.x == 0) {
+        tma_bar_init(&bars[0]); tma_bar_init(&bars[1]);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if ((long long)blockIdx.x < total) issue(blockIdx.x, 0);
+    }
+    __syncthreads();
+
+    const int cvl = threadIdx.x & 7, pl = threadIdx.x >> 3;                 // channel vector inside the block, patch inside the tile
+    const int ptx = pl & 7, pty = pl >> 3;                                  // 8 x 4 patches of 4 x 4 pixels
+    int it = 0;
+    for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int cur = it & 1;
+        const long long nxt = t + gridDim.x;
+        if (threadIdx.x == 0 && nxt < total) issue(nxt, cur ^ 1);           // buffer cur^1 was released by the __syncthreads below
+        int n, cb, ox_t, oy_t;
+        coords(t, n, cb, ox_t, oy_t);
+        tma_bar_wait(&bars[cur], (it >> 1) & 1);
+        const T* tile = reinterpret_cast<const T*>(base + cur * GM::kTileBytes) + ((pty * AY::kStep) * GM::BW + ptx * AX::kStep) * kClCB + cvl * 4;
+        const int ox0 = ox_t + ptx * kPatch, oy0 = oy_t + pty * kPatch;
+        if (ox0 < p.out_w && oy0 < p.out_h)
+            cl_patch_body<T, UX, UY, DX, DY, FW, FH, PHX, PHY, kEpi>(p, fk, n, cb * (kClCB / 4) + cvl, ox0, oy0, [&](int r, int q, float (&w)[4]) {
+                V4s<T>::ld(tile + (r * GM::BW + q) * kClCB, w);
+            });
+        __syncthreads();
     }
 }
 
 template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+static int launch_cl_tma(const UpfirArgs& p, cudaStream_t st_) {
+    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    CUtensorMap map;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.in_c, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.in_n};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.isw * sizeof(T), (cuuint64_t)p.ish * sizeof(T), (cuuint64_t)p.isn * sizeof(T)};
+    const cuuint32_t box[4] = {(cuuint32_t)kClCB, (cuuint32_t)GM::BW, (cuuint32_t)GM::BH, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = encode_tiled()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+                                      const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: cuTensorMapEncodeTiled (channels_last) failed (%d)", (int)r);
+    void (*kern)(const UpfirArgs, int, int, int, const CUtensorMap) = p.epi ? upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, true>
+                                                                            : upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, false>;
+    const size_t smem = GM::kSmem;
+    if (smem > 48 * 1024) IDE3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles_x = ceil_div(p.out_w, kClTileW), tiles_y = ceil_div(p.out_h, kClTileH), cblocks = p.in_c / kClCB;
+    const long long total = (long long)tiles_x * tiles_y * cblocks * p.in_n;
+    int per_sm = 1;
+    IDE3D_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem));
+    if (per_sm < 1) per_sm = 1;
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > total) grid = total;
+    kern<<<(unsigned)grid, 256, smem, st_>>>(p, tiles_x, tiles_y, cblocks, map);
+    IDE3D_CHECK_LAUNCH("upfirdn2d_cl_tma_kernel");
+    return IDE3D_OK;
+}
+
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
 static int launch_cl_patch(const UpfirArgs& p, cudaStream_t st_) {
+    // TMA-staged tiles when the tensor map can describe the input (C % 32 == 0, 16-byte aligned base and pitches) and two
+    // input boxes fit one SM; IDE3D_TMA=0 keeps the L1-gather kernel below.
+    if constexpr (ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kSmem <= 200 * 1024) {
+        const char* tma_env = getenv("IDE3D_TMA");
+        const bool ok = !(tma_env != nullptr && tma_env[0] == '0') && encode_tiled() != nullptr && p.in_c % kClCB == 0 &&
+                        (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (p.isw * sizeof(T)) % 16 == 0 && (p.ish * sizeof(T)) % 16 == 0 &&
+                        (p.isn * sizeof(T)) % 16 == 0 && p.out_w * (long long)p.out_h >= 64;
+        if (ok) {
+            const int rc = launch_cl_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY>(p, st_);
+            if (rc != IDE3D_UNSUPPORTED) return rc;
+        }
+    }
     const int patches_x = ceil_div(p.out_w, kPatch), patches_y = ceil_div(p.out_h, kPatch);
     const long long total = (long long)patches_x * patches_y * p.in_n * (p.in_c >> 2);
     long long grid = ceil_div<long long>(total, 256);

@@ -337,12 +337,14 @@ def test_upfirdn2d_channels_last_kernel_matches_contiguous_bitwise_shape():
 
 @pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2)])
 @pytest.mark.parametrize('hw', [(64, 64), (37, 70), (5, 3)])
-def test_upfirdn2d_channels_last_patch_kernel_phases(dtype, atol, rtol, hw):
-    """channels_last + C % 4 == 0 + the 4x4 StyleGAN2 filter -> upfirdn2d_cl_patch_kernel; every padding phase, ragged
-    edges, negative padding (cropping) and sliced (non-dense) channel ranges."""
+@pytest.mark.parametrize('C,lo', [(12, 4), (96, 32)])
+def test_upfirdn2d_channels_last_patch_kernel_phases(dtype, atol, rtol, hw, C, lo):
+    """channels_last + the 4x4 StyleGAN2 filter: C % 4 == 0 -> upfirdn2d_cl_patch_kernel (L1 gather), C % 32 == 0 ->
+    upfirdn2d_cl_tma_kernel (TMA-staged tiles); every padding phase, ragged edges, negative padding (cropping) and sliced
+    (non-dense) channel ranges."""
     from ide3d_b200.torch_utils.ops import upfirdn2d as up
     g = torch.Generator().manual_seed(13)
-    x = torch.randn(2, 12, *hw, generator=g).to(dtype)
+    x = torch.randn(2, C, *hw, generator=g).to(dtype)
     f4 = oops.setup_filter([1, 3, 3, 1])
     cases = [dict(up=2, padding=[2, 1, 2, 1], gain=4), dict(up=2, padding=[1, 2, 2, 1], gain=4), dict(up=2, padding=[3, 0, 1, 2]),
              dict(up=2, padding=[2, 1, 1, 2]), dict(padding=[1, 1, 1, 1], gain=4), dict(padding=[2, 1, 0, 3]), dict(padding=[-1, 4, 3, -1]),
@@ -355,40 +357,42 @@ def test_upfirdn2d_channels_last_patch_kernel_phases(dtype, atol, rtol, hw):
         y = up.upfirdn2d(xc, f4.to(DEV), **kw)
         assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
         assert_close(y, ref, atol, rtol, what=str(kw))
-        ys = up.upfirdn2d(xc[:, 4:12], f4.to(DEV), **kw)              # channel slice: stride_c == 1, pixel pitch 12
-        assert_close(ys, ref[:, 4:12], atol, rtol, what='slice ' + str(kw))
+        ys = up.upfirdn2d(xc[:, lo:C], f4.to(DEV), **kw)              # channel slice: stride_c == 1, pixel pitch C
+        assert_close(ys, ref[:, lo:C], atol, rtol, what='slice ' + str(kw))
 
 
 @pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 2e-5, 0), (torch.float16, 2e-2, 1e-2)])
-def test_upsample2d_add_is_upsample_then_add(dtype, atol, rtol):
+@pytest.mark.parametrize('CI,CW,lo', [(8, 20, 4), (32, 96, 64)])
+def test_upsample2d_add_is_upsample_then_add(dtype, atol, rtol, CI, CW, lo):
     """Skip-connection step in one pass == upsample2d (networks.py:841) + add (:844) + ToRGB bias (:707); `y` may be a channel
     slice of a wider NHWC tensor.  NCHW inputs take the composed path and give the same values."""
     from ide3d_b200.torch_utils.ops import upfirdn2d as up
     g = torch.Generator().manual_seed(21)
-    img = torch.randn(2, 8, 9, 13, generator=g).to(dtype)
-    ywide = torch.randn(2, 20, 18, 26, generator=g).to(dtype)
-    b = torch.randn(8, generator=g).to(dtype)
+    img = torch.randn(2, CI, 9, 13, generator=g).to(dtype)
+    ywide = torch.randn(2, CW, 18, 26, generator=g).to(dtype)
+    b = torch.randn(CI, generator=g).to(dtype)
     f = oops.setup_filter([1, 3, 3, 1])
-    want = oops.upsample2d(img.double(), f) + ywide[:, 4:12].double() + b.double().reshape(1, -1, 1, 1)
+    want = oops.upsample2d(img.double(), f) + ywide[:, lo:lo + CI].double() + b.double().reshape(1, -1, 1, 1)
     yd = ywide.to(DEV).contiguous(memory_format=torch.channels_last)
     keep = yd.clone()
-    out = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, 4:12], b.to(DEV))
+    out = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, lo:lo + CI], b.to(DEV))
     assert out.is_contiguous(memory_format=torch.channels_last) and torch.equal(yd, keep)
     assert_close(out, want, atol, rtol)
-    out2 = up.upsample2d_add(img.to(DEV), f.to(DEV), ywide[:, 4:12].to(DEV), b.to(DEV))          # NCHW: composed
+    out2 = up.upsample2d_add(img.to(DEV), f.to(DEV), ywide[:, lo:lo + CI].to(DEV), b.to(DEV))          # NCHW: composed
     assert_close(out2, want, atol, rtol)
-    out3 = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, 4:12], None)
+    out3 = up.upsample2d_add(img.to(DEV).contiguous(memory_format=torch.channels_last), f.to(DEV), yd[:, lo:lo + CI], None)
     assert_close(out3, want - b.double().reshape(1, -1, 1, 1), atol, rtol)
 
 
 @pytest.mark.parametrize('dtype,atol,rtol', [(torch.float32, 3e-5, 1e-5), (torch.float16, 3e-2, 2e-2)])
 @pytest.mark.parametrize('act,noise_kind', [('lrelu', 'const'), ('lrelu', 'batch'), ('linear', None), ('tanh', 'const')])
-def test_upfirdn2d_epilogue_is_fir_then_modconv_tail(dtype, atol, rtol, act, noise_kind):
+@pytest.mark.parametrize('C', [8, 64])
+def test_upfirdn2d_epilogue_is_fir_then_modconv_tail(dtype, atol, rtol, act, noise_kind, C):
     """FIR + demodulation/noise/bias_act in one pass == conv2d_resample.py:125 followed by networks.py:104-105, :512.
     ('tanh' is not fused by the kernel: the op composes upfirdn2d + scaled_bias_act and must give the same values.)"""
     from ide3d_b200.torch_utils.ops import upfirdn2d as up
     g = torch.Generator().manual_seed(31)
-    N, C, H, W = 2, 8, 19, 23                        # transposed-conv output of a 9x11 layer: (2r+1)
+    N, H, W = 2, 19, 23                              # transposed-conv output of a 9x11 layer: (2r+1)
     x = torch.randn(N, C, H, W, generator=g).to(dtype)
     f = oops.setup_filter([1, 3, 3, 1])
     pad = [1, 1, 1, 1]
