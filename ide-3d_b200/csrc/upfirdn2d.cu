@@ -607,15 +607,21 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
 // (channels x columns x rows of a 4-D tensor map, zero-filled outside the image by the TMA unit) arrives with ONE
 // cp.async.bulk.tensor.4d per tile, double-buffered against the FIR of the previous tile.  Shared-memory pixels are 128-byte
 // (fp32) runs of 32 channels, so the 8 lanes that share a patch read one contiguous line per window element.
-constexpr int kClTileW = 32, kClTileH = 16, kClCB = 32;
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+// Tile shapes: CB channels x (PX x PY patches of 4 x 4 pixels), CB/4 * PX * PY = 256 threads.  The TMA unit is fed one
+// innermost run (CB channels) per request, so wider channel blocks move more bytes per request: 64 channels x 16x16 pixels
+// when C % 64 == 0, else 32 channels x 32x16 pixels.
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, int CB>
 struct ClTmaGeom {
     using AX = Axis<UX, DX, FW, PHX>;
     using AY = Axis<UY, DY, FH, PHY>;
-    static constexpr int BW = (kClTileW / kPatch - 1) * AX::kStep + AX::kWin;
-    static constexpr int BH = (kClTileH / kPatch - 1) * AY::kStep + AY::kWin;
-    static constexpr int kTileBytes = ((BW * BH * kClCB * (int)sizeof(T) + 127) / 128) * 128;
+    static constexpr int kCB = CB, kCV = CB / 4;
+    static constexpr int PX = (CB == 32) ? 8 : 4, PY = 256 / (kCV * PX);
+    static constexpr int kTileW = PX * kPatch, kTileH = PY * kPatch;
+    static constexpr int BW = (PX - 1) * AX::kStep + AX::kWin;
+    static constexpr int BH = (PY - 1) * AY::kStep + AY::kWin;
+    static constexpr int kTileBytes = ((BW * BH * CB * (int)sizeof(T) + 127) / 128) * 128;
     static constexpr int kSmem = 2 * kTileBytes + 128 + 128;
+    static_assert(kCV * PX * PY == 256, "one thread per (channel vector, patch)");
 };
 __device__ __forceinline__ void tma_load_tile4(void* dst, const CUtensorMap* map, unsigned long long* bar, int c, int x, int y, int n, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
@@ -634,10 +640,11 @@ template <> struct V4s<__half> {
     }
 };
 
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi>
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi, int CB>
 __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p, int tiles_x, int tiles_y, int cblocks,
                                                                const __grid_constant__ CUtensorMap tmap) {
-    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, CB>;
+    constexpr int kClCB = CB, kClTileW = GM::kTileW, kClTileH = GM::kTileH;
     using AX = typename GM::AX;
     using AY = typename GM::AY;
     extern __shared__ unsigned char tma_raw[];
@@ -669,8 +676,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p
     }
     __syncthreads();
 
-    const int cvl = threadIdx.x & 7, pl = threadIdx.x >> 3;                 // channel vector inside the block, patch inside the tile
-    const int ptx = pl & 7, pty = pl >> 3;                                  // 8 x 4 patches of 4 x 4 pixels
+    const int cvl = threadIdx.x % GM::kCV, pl = threadIdx.x / GM::kCV;       // channel vector inside the block, patch inside the tile
+    const int ptx = pl % GM::PX, pty = pl / GM::PX;
     int it = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int cur = it & 1;
@@ -689,9 +696,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p
     }
 }
 
-template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY>
+template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, int CB>
 static int launch_cl_tma(const UpfirArgs& p, cudaStream_t st_) {
-    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>;
+    using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, CB>;
+    constexpr int kClCB = CB, kClTileW = GM::kTileW, kClTileH = GM::kTileH;
     CUtensorMap map;
     const cuuint64_t dims[4] = {(cuuint64_t)p.in_c, (cuuint64_t)p.in_w, (cuuint64_t)p.in_h, (cuuint64_t)p.in_n};
     const cuuint64_t strides[3] = {(cuuint64_t)p.isw * sizeof(T), (cuuint64_t)p.ish * sizeof(T), (cuuint64_t)p.isn * sizeof(T)};
@@ -701,8 +709,8 @@ static int launch_cl_tma(const UpfirArgs& p, cudaStream_t st_) {
                                       const_cast<void*>(p.x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                       CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) IDE3D_FAIL(IDE3D_UNSUPPORTED, "upfirdn2d: cuTensorMapEncodeTiled (channels_last) failed (%d)", (int)r);
-    void (*kern)(const UpfirArgs, int, int, int, const CUtensorMap) = p.epi ? upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, true>
-                                                                            : upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, false>;
+    void (*kern)(const UpfirArgs, int, int, int, const CUtensorMap) = p.epi ? upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, true, CB>
+                                                                            : upfirdn2d_cl_tma_kernel<T, UX, UY, DX, DY, FW, FH, PHX, PHY, false, CB>;
     const size_t smem = GM::kSmem;
     if (smem > 48 * 1024) IDE3D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles_x = ceil_div(p.out_w, kClTileW), tiles_y = ceil_div(p.out_h, kClTileH), cblocks = p.in_c / kClCB;
@@ -721,13 +729,20 @@ template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, i
 static int launch_cl_patch(const UpfirArgs& p, cudaStream_t st_) {
     // TMA-staged tiles when the tensor map can describe the input (C % 32 == 0, 16-byte aligned base and pitches) and two
     // input boxes fit one SM; IDE3D_TMA=0 keeps the L1-gather kernel below.
-    if constexpr (ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kSmem <= 200 * 1024) {
+    // Measured (scripts/bench_ops.py, [1,512,512,512] fp32): the up=1 FIR runs at 87 % of the HBM peak from TMA tiles (46 % from
+    // the L1-gather kernel); 2x upsampling has only 2x2 live taps per output and is faster straight from L1 (85 % vs 80 %).
+    if constexpr (UX == 1 && UY == 1 && ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, 32>::kSmem <= 200 * 1024) {
         const char* tma_env = getenv("IDE3D_TMA");
-        const bool ok = !(tma_env != nullptr && tma_env[0] == '0') && encode_tiled() != nullptr && p.in_c % kClCB == 0 &&
+        const char* cb_env = getenv("IDE3D_CL_CB");                         // experiments: force the 32-channel tile shape
+        const bool ok = !(tma_env != nullptr && tma_env[0] == '0') && encode_tiled() != nullptr && p.in_c % 32 == 0 &&
                         (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (p.isw * sizeof(T)) % 16 == 0 && (p.ish * sizeof(T)) % 16 == 0 &&
                         (p.isn * sizeof(T)) % 16 == 0 && p.out_w * (long long)p.out_h >= 64;
         if (ok) {
-            const int rc = launch_cl_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY>(p, st_);
+            int rc = IDE3D_UNSUPPORTED;
+            if constexpr (ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, 64>::kSmem <= 200 * 1024) {
+                if (p.in_c % 64 == 0 && !(cb_env != nullptr && cb_env[0] == '3')) rc = launch_cl_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY, 64>(p, st_);
+            }
+            if (rc == IDE3D_UNSUPPORTED) rc = launch_cl_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY, 32>(p, st_);
             if (rc != IDE3D_UNSUPPORTED) return rc;
         }
     }
