@@ -10,7 +10,7 @@ sweep -- BASELINE.json configs[1].  Weak scaling: every rank renders its own 8-f
 
 value : whole-job frames/s with ws / cameras already resident in HBM (CUDA events, max over ranks, L2 flushed
         between timed iterations).
-e2e   : the same metric through the public call a user makes (render_frames_sharded: host ws / cameras -> H2D from
+e2e   : the same metric through the public call a user makes (stream_frames_sharded: host ws / cameras -> H2D from
         pinned memory -> synthesis -> uint8 frames -> all_gather over NCCL when N > 1 -> D2H), copies inside the
         timed region.
 roofline : the fused ray-march kernel (dominant kernel of the renderer), timed live with CUDA events on its stream
@@ -232,22 +232,20 @@ def main():
     def step():
         return G.synthesis(ws, c=c, **kw)
 
-    # pinned host buffers for the e2e leg
-    ws_pin = ws.cpu().pin_memory()
-    c_pin = c_host.pin_memory()
+    # e2e leg: ONE public call renders steps x world x 8 frames from pinned host ws / c; every batch's inputs are uploaded and
+    # its uint8 frames gathered over the ranks and downloaded to pinned host memory inside the timed region (the download of
+    # batch i overlaps the rendering of batch i+1 -- the frame loop of gen_videos.py as a pipeline).
+    def e2e_inputs(steps):
+        reps = steps * world
+        return ws.cpu().repeat(reps, 1, 1).pin_memory(), c_host.repeat(reps, 1).pin_memory()
 
-    def step_e2e():
-        frames = idist.render_frames_sharded(G, ws_pin, c_pin, 0, 1, batch=BATCH, **kw)     # this rank's 8 frames
-        if world > 1:
-            allf = torch.empty((world * frames.shape[0],) + tuple(frames.shape[1:]), dtype=frames.dtype, device=device)
-            tdist.all_gather_into_tensor(allf, frames)
-            frames = allf if rank == 0 else frames
-        return frames.cpu() if rank == 0 else frames
+    def run_e2e(ws_pin, c_pin):
+        return idist.stream_frames_sharded(G, ws_pin, c_pin, rank, world, batch=BATCH, **kw)
 
     with torch.no_grad():
         for _ in range(max(args.warmup, 3)):
             step()
-        step_e2e()
+        run_e2e(*e2e_inputs(2))
         barrier()
 
         # ---------------- value: device-resident inputs, per-iteration events, L2 flushed between iterations
@@ -271,15 +269,14 @@ def main():
         kern_ms = float(np.mean([a.elapsed_time(b) for a, b, _ in kern]))
 
         # ---------------- e2e: host inputs, copies inside the timed region
-        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        ws_pin, c_pin = e2e_inputs(args.steps)
+        run_e2e(ws_pin, c_pin)                      # allocates the pinned result buffer of this size once
         barrier()
         t0 = time.perf_counter()
-        for a, b in ev2:
-            a.record()
-            step_e2e()
-            b.record()
+        frames_host = run_e2e(ws_pin, c_pin)        # returns after the last frame is in host memory
         barrier()
         e2e_wall = time.perf_counter() - t0
+        assert rank != 0 or (frames_host.shape[0] == args.steps * world * BATCH and frames_host.device.type == 'cpu')
 
         # ---------------- renderer only (planes resident, channels-last): the kernel's own throughput per frame
         voxel_ws, _ = G.synthesis.split_ws(ws)
@@ -313,8 +310,8 @@ def main():
                                    'random-init ide3d-ffhq-64-512 (TriPlaneGenerator seed 0)',
                        'frames_per_step_per_gpu': BATCH, 'plane': [96, PLANE, PLANE], 'l2': 'flushed (256 MB write) between timed iterations',
                        'timing': 'CUDA events per iteration on the launching stream, max over ranks', 'parallelism': f'frames sharded x{world}, no data-path collective'},
-            'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int(ws_pin.numel() * 4 + c_pin.numel() * 4),
-                    'd2h_bytes_per_step': int(BATCH * world * 3 * 512 * 512), 'call': 'ide3d_b200.dist.render_frames_sharded (pinned host ws/c -> uint8 frames on host)'},
+            'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int((ws_pin.numel() * 4 + c_pin.numel() * 4) // args.steps),
+                    'd2h_bytes_per_step': int(BATCH * world * 3 * 512 * 512), 'call': 'ide3d_b200.dist.stream_frames_sharded (pinned host ws/c -> uint8 frames in pinned host memory; D2H of batch i overlaps batch i+1)'},
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'raymarch_tc_kernel (fused gather + tcgen05 decoder MLP + compositing)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': RAYMARCH_DRAM_BYTES_NCU, 'traffic_source': 'profiles/r01_ncu_raymarch_tc.txt (dram__bytes_read+write, one ncu --set full capture of this launch)', 'peak_source': peak_src, 'kernel_ms': kern_ms,

@@ -620,7 +620,11 @@ struct ClTmaGeom {
     static constexpr int BW = (PX - 1) * AX::kStep + AX::kWin;
     static constexpr int BH = (PY - 1) * AY::kStep + AY::kWin;
     static constexpr int kTileBytes = ((BW * BH * CB * (int)sizeof(T) + 127) / 128) * 128;
-    static constexpr int kSmem = 2 * kTileBytes + 128 + 128;
+    // Two blocks per SM (16 warps) hide the FIR's issue latency better than one block with a deeper ring (measured: one
+    // 8-warp block issues 42 % of its slots): small boxes are double-buffered inside the block, large ones (the 92 KB box of
+    // the up=1 FIR) rely on the co-resident block to overlap their load.
+    static constexpr int kStages = (2 * kTileBytes + 256 <= 110 * 1024) ? 2 : 1;
+    static constexpr int kSmem = kStages * kTileBytes + 128 + 128;
     static_assert(kCV * PX * PY == 256, "one thread per (channel vector, patch)");
 };
 __device__ __forceinline__ void tma_load_tile4(void* dst, const CUtensorMap* map, unsigned long long* bar, int c, int x, int y, int n, unsigned bytes) {
@@ -641,7 +645,7 @@ template <> struct V4s<__half> {
 };
 
 template <typename T, int UX, int UY, int DX, int DY, int FW, int FH, int PHX, int PHY, bool kEpi, int CB>
-__global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p, int tiles_x, int tiles_y, int cblocks,
+__global__ void __launch_bounds__(256, 2) upfirdn2d_cl_tma_kernel(const UpfirArgs p, int tiles_x, int tiles_y, int cblocks,
                                                                const __grid_constant__ CUtensorMap tmap) {
     using GM = ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, CB>;
     constexpr int kClCB = CB, kClTileW = GM::kTileW, kClTileH = GM::kTileH;
@@ -649,7 +653,8 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p
     using AY = typename GM::AY;
     extern __shared__ unsigned char tma_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tma_raw) + 127) & ~(uintptr_t)127);
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + 2 * GM::kTileBytes);
+    constexpr int NST = GM::kStages;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(base + NST * GM::kTileBytes);
     float fk[FH][FW];
     load_filter<FW, FH>(p, fk);
     const int ax = floor_div(p.px0, UX), ay = floor_div(p.py0, UY);
@@ -670,9 +675,10 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p
                        oy_t * DY / UY - ay + AY::lo(), n, kBytes);
     };
     if (threadIdx.x == 0) {
-        tma_bar_init(&bars[0]); tma_bar_init(&bars[1]);
+        for (int i = 0; i < NST; ++i) tma_bar_init(&bars[i]);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        if ((long long)blockIdx.x < total) issue(blockIdx.x, 0);
+        for (int i = 0; i < NST; ++i)
+            if ((long long)blockIdx.x + (long long)i * gridDim.x < total) issue((long long)blockIdx.x + (long long)i * gridDim.x, i);
     }
     __syncthreads();
 
@@ -680,19 +686,19 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_tma_kernel(const UpfirArgs p
     const int ptx = pl % GM::PX, pty = pl / GM::PX;
     int it = 0;
     for (long long t = blockIdx.x; t < total; t += gridDim.x, ++it) {
-        const int cur = it & 1;
-        const long long nxt = t + gridDim.x;
-        if (threadIdx.x == 0 && nxt < total) issue(nxt, cur ^ 1);           // buffer cur^1 was released by the __syncthreads below
+        const int cur = it % NST;
         int n, cb, ox_t, oy_t;
         coords(t, n, cb, ox_t, oy_t);
-        tma_bar_wait(&bars[cur], (it >> 1) & 1);
+        tma_bar_wait(&bars[cur], (it / NST) & 1);
         const T* tile = reinterpret_cast<const T*>(base + cur * GM::kTileBytes) + ((pty * AY::kStep) * GM::BW + ptx * AX::kStep) * kClCB + cvl * 4;
         const int ox0 = ox_t + ptx * kPatch, oy0 = oy_t + pty * kPatch;
         if (ox0 < p.out_w && oy0 < p.out_h)
             cl_patch_body<T, UX, UY, DX, DY, FW, FH, PHX, PHY, kEpi>(p, fk, n, cb * (kClCB / 4) + cvl, ox0, oy0, [&](int r, int q, float (&w)[4]) {
                 V4s<T>::ld(tile + (r * GM::BW + q) * kClCB, w);
             });
-        __syncthreads();
+        __syncthreads();                                                     // every thread is done with stage `cur`
+        const long long nxt = t + (long long)NST * gridDim.x;
+        if (threadIdx.x == 0 && nxt < total) issue(nxt, cur);
     }
 }
 

@@ -94,6 +94,65 @@ def render_frames_sharded(G, ws, c, rank, world, batch=8, to_uint8=True, **synth
     return all_gather_padded(local, F, world)
 
 
+_pinned = {}
+
+
+def _pinned_buffer(shape, dtype):
+    """Page-locked host buffer, cached per (shape, dtype): cudaHostAlloc costs milliseconds, a frame batch does not."""
+    key = (tuple(shape), dtype)
+    buf = _pinned.get(key)
+    if buf is None:
+        buf = _pinned[key] = torch.empty(shape, dtype=dtype, pin_memory=torch.cuda.is_available())
+    return buf
+
+
+@torch.no_grad()
+def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, **synthesis_kwargs):
+    """The frame loop of gen_videos.py:127-139 as a pipeline: frames i = rank, rank+world, ... are rendered in batches;
+    every batch is gathered over the ranks (one all_gather of uint8 frames) and copied to page-locked HOST memory on a side
+    stream while the next batch renders.  ws [F, num_ws, w_dim], c [F, 25] on the host (pinned for asynchronous uploads).
+    Returns uint8 [F, 3, H, W] on the host on rank 0 (a cached pinned buffer unless `out` is given), None elsewhere.
+    F must be a multiple of world * batch."""
+    F = ws.shape[0]
+    assert F % (world * batch) == 0, 'stream_frames_sharded: F must be a multiple of world * batch'
+    dev = next(G.parameters()).device
+    cuda = dev.type == 'cuda'
+    shape = (F, G.img_channels, G.img_resolution, G.img_resolution)
+    host = None
+    if rank == 0:
+        host = out if out is not None else _pinned_buffer(shape, torch.uint8)
+    copy_stream = torch.cuda.Stream(dev) if cuda else None
+    per_rank = F // world
+    for b0 in range(0, per_rank, batch):
+        if world == 1:
+            w_b, c_b = ws[b0:b0 + batch], c[b0:b0 + batch]                   # views of the pinned inputs: asynchronous H2D
+        else:
+            sel = torch.arange(rank + world * b0, rank + world * (b0 + batch), world)
+            w_b, c_b = ws[sel], c[sel]
+        img = G.synthesis(w_b.to(dev, non_blocking=True), c=c_b.to(dev, non_blocking=True), **synthesis_kwargs)
+        if isinstance(img, (tuple, list)):
+            img = img[0]
+        img = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).contiguous()
+        if world > 1:
+            allf = torch.empty((world,) + tuple(img.shape), dtype=img.dtype, device=dev)
+            dist.all_gather_into_tensor(allf.view((world * img.shape[0],) + tuple(img.shape[1:])), img)
+            img = allf.transpose(0, 1).reshape((world * batch,) + tuple(img.shape[1:]))     # frame order: j * world + r
+        if rank == 0:
+            lo = world * b0
+            if cuda:
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    host[lo:lo + world * batch].copy_(img, non_blocking=True)
+                img.record_stream(copy_stream)
+            else:
+                host[lo:lo + world * batch].copy_(img)
+    if cuda:
+        if copy_stream is not None:
+            copy_stream.synchronize()
+        torch.cuda.current_stream(dev).synchronize()
+    return host
+
+
 @torch.no_grad()
 def sigma_grid_sharded(G, img_v, seg_v, rank, world, grid_n=256, cube_length=1.0, voxel_origin=(0, 0, 0)):
     """extract_shapes' density grid, flat voxel range split into contiguous z-slabs over the ranks, one all_gather."""

@@ -24,6 +24,7 @@ class PackedDecoder:
     def __init__(self, heads, device):
         assert 1 <= len(heads) <= 4
         self.tensors = []
+        self.meta = [(int(h[0]), int(h[1])) for h in heads]          # (in_sel, out_offset) per head
         self.struct = L.Decoder()
         self.struct.num_heads = len(heads)
         for i, (in_sel, out_off, w1, b1, w2, b2) in enumerate(heads):
@@ -66,7 +67,40 @@ def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), nu
              return_weights=False, convert_layout=True, precision='auto'):
     """Fused render of N frames.  -> feat [N,R,51], depth [N,R,1], weights [N,R,S,1] | None.
     jitter_u: explicit uniforms [N,R,S]; jitter_seed: in-kernel counter hash; neither: no jitter.
-    precision: 'auto' | 'fp32' (CUDA-core FFMA decoder) | 'tc' (tcgen05 decoder, bf16x3 products)."""
+    precision: 'auto' | 'fp32' (CUDA-core FFMA decoder) | 'tc' (tcgen05 decoder, bf16x3 products).
+    Differentiable w.r.t. the planes, the camera and the decoder parameters (when `decoder` is a list of heads holding the
+    live parameters): the forward is the same fused kernel, the backward is render_grad.RaymarchFunction."""
+    kw = dict(resolution=resolution, num_steps=num_steps, fov=fov, ray_start=ray_start, ray_end=ray_end, box_scale=box_scale,
+              jitter_seed=jitter_seed, noise_std=noise_std, clamp_mode=clamp_mode, last_back=last_back, white_back=white_back,
+              max_depth=max_depth, fill_mode=fill_mode, return_weights=return_weights, convert_layout=convert_layout, precision=precision)
+    if isinstance(decoder, PackedDecoder):
+        meta, params = decoder.meta, list(decoder.tensors)
+    else:
+        meta, params = [(int(h[0]), int(h[1])) for h in decoder], [t for h in decoder for t in h[2:6]]
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in [planes_tex, planes_seg, cam2world] + params):
+        from . import render_grad
+        if clamp_mode not in ('softplus', 'relu'):
+            raise ValueError('Need to choose clamp mode')
+        W, H = (resolution, resolution) if isinstance(resolution, int) else resolution
+        cfg = dict(W=int(W), H=int(H), S=int(num_steps), fov=float(fov), ray_start=float(ray_start), ray_end=float(ray_end),
+                   box_scale=float(box_scale), jitter_seed=None if jitter_u is not None else jitter_seed, noise_std=float(noise_std or 0.0),
+                   clamp_mode=clamp_mode, last_back=bool(last_back), white_back=bool(white_back), max_depth=float(max_depth or 0.0),
+                   fill_weight=(fill_mode == 'weight'))
+
+        def fwd(tex, seg, heads, cam, ju, nz):
+            return _raymarch_impl(tex, seg, heads, cam, jitter_u=ju, noise=nz, **kw)
+
+        n = planes_tex.shape[0]
+        feat, depth, weights = render_grad.RaymarchFunction.apply(fwd, cfg, meta, jitter_u, noise, bool(return_weights), planes_tex.float(),
+                                                                  planes_seg.float(), cam2world.reshape(n, 4, 4).float(), *params)
+        return feat, depth, (weights if return_weights else None)
+    return _raymarch_impl(planes_tex, planes_seg, decoder, cam2world, jitter_u=jitter_u, noise=noise, **kw)
+
+
+def _raymarch_impl(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, fov=18.0, ray_start=2.25,
+                   ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
+                   clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None,
+                   return_weights=False, convert_layout=True, precision='auto'):
     if clamp_mode not in ('softplus', 'relu'):
         raise ValueError('Need to choose clamp mode')
     if fill_mode not in (None, 'weight'):

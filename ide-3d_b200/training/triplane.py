@@ -110,7 +110,9 @@ class TriPlaneRenderer(torch.nn.Module):
         if perturb in (None, False, 'none'):
             seed = None
         noise = torch.randn([n, res[0] * res[1], num_steps], device=img_v.device) if nerf_noise else None
-        return render.raymarch(img_v, seg_v, self.packed(), cam2world, resolution=res, num_steps=num_steps, fov=fov,
+        # live parameters (differentiable) when a gradient can reach them, else the cached device copy
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        return render.raymarch(img_v, seg_v, self.heads() if train else self.packed(), cam2world, resolution=res, num_steps=num_steps, fov=fov,
                                ray_start=ray_start, ray_end=ray_end, box_scale=self.box_scale, jitter_u=jitter_u,
                                jitter_seed=seed, noise=noise, noise_std=float(nerf_noise or 0.0), clamp_mode=clamp_mode,
                                last_back=last_back, white_back=white_back, max_depth=max_depth, fill_mode=fill_mode,

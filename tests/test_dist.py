@@ -29,6 +29,9 @@ def _worker(rank, world, port, q):
         ws = G.mapping(z, c)
         frames = idist.render_frames_sharded(G, ws, c, rank, world, batch=2, num_steps=6, perturb=None)
         single = idist.render_frames_sharded(G, ws, c, 0, 1, batch=8, num_steps=6, perturb=None)
+        # streaming variant (the e2e leg of bench.py): F multiple of world * batch, result on the host of rank 0 only
+        streamed = idist.stream_frames_sharded(G, ws[:4], c[:4], rank, world, batch=2, num_steps=6, perturb=None)
+        sdiff = int((streamed.int() - single[:4].int()).abs().max()) if rank == 0 else (0 if streamed is None else 99)
     # voxel slabs: every rank fills its contiguous slab of a fake sigma volume, one all_gather restores the volume
     total = 4 ** 3 + 1
     first, count = idist.slab_range(total, rank, world)
@@ -36,7 +39,7 @@ def _worker(rank, world, port, q):
     vol = idist.all_gather_slabs(local, total, world)
     # different batch compositions may pick different CPU conv algorithms: allow one uint8 level
     diff = int((frames.int() - single.int()).abs().max())
-    q.put((rank, frames.shape, diff, bool(torch.equal(vol[0], torch.arange(total, dtype=torch.float32)))))
+    q.put((rank, frames.shape, max(diff, sdiff), bool(torch.equal(vol[0], torch.arange(total, dtype=torch.float32)))))
     dist.barrier()
     dist.destroy_process_group()
 

@@ -1,0 +1,97 @@
+"""Backward of the renderer.  The forward is the fused kernel; the backward re-evaluates the chain with
+torch library ops (ide3d_b200.render_grad.composed_chain).  Checked against autograd through the oracle's restatement of the
+reference functions: on CPU (chain values, slab invariance, gradients) and on the GPU (the autograd.Function end to end)."""
+
+import pytest
+import torch
+
+from oracle import renderer as orr
+from test_gpu_renderer import _random_case, three_head_from_dense
+
+S, RES = 12, (6, 5)
+
+
+def _cfg(**opts):
+    return dict(W=RES[0], H=RES[1], S=S, fov=18.0, ray_start=2.25, ray_end=3.3, box_scale=2.0, jitter_seed=opts.get('jitter_seed'),
+                noise_std=0.0, clamp_mode=opts.get('clamp_mode', 'softplus'), last_back=opts.get('last_back', False),
+                white_back=opts.get('white_back', False), max_depth=opts.get('max_depth', 0.0), fill_weight=opts.get('fill_mode') == 'weight')
+
+
+def _oracle_grads(tex, seg, dec, cam, u, gf, gd, **opts):
+    t, s, c = tex.clone().requires_grad_(True), seg.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+    params = [p.clone().requires_grad_(True) for p in (dec.w1, dec.b1, dec.w2, dec.b2)]
+    rgb, depth, _ = orr.render_frames(t, s, orr.Decoder(*params), c, num_steps=S, resolution=RES, jitter_u=u, **opts)
+    (rgb * gf).sum().add((depth * gd).sum()).backward()
+    return rgb.detach(), depth.detach(), t.grad, s.grad, c.grad, [p.grad for p in params]
+
+
+@pytest.mark.parametrize('opts', [dict(), dict(white_back=True, max_depth=3.3, last_back=True), dict(clamp_mode='relu')])
+def test_composed_chain_matches_oracle_values_and_gradients_cpu(opts):
+    from ide3d_b200 import render_grad as rg
+    tex, seg, dec, cam = _random_case(2, 16, seed=4)
+    g = torch.Generator().manual_seed(1)
+    u = torch.rand(2, RES[0] * RES[1], S, 1, generator=g)
+    gf, gd = torch.randn(2, 30, 51, generator=g), torch.randn(2, 30, 1, generator=g)
+    rgb, depth, gt, gs, gc, gp = _oracle_grads(tex, seg, dec, cam, u, gf, gd, **opts)
+
+    heads = [tuple(h[:2]) + tuple(t.clone().requires_grad_(True) for t in h[2:]) for h in three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)]
+    t, s, c = tex.clone().requires_grad_(True), seg.clone().requires_grad_(True), cam.clone().requires_grad_(True)
+    f, d, w = rg.composed_chain(t, s, heads, c, _cfg(**opts), jitter_u=u)
+    assert (f - rgb).abs().max() < 3e-5 and (d - depth).abs().max() < 1e-5
+    slabs = torch.cat([rg.composed_chain(t, s, heads, c, _cfg(**opts), jitter_u=u, rays=(r0, min(7, 30 - r0)))[0] for r0 in range(0, 30, 7)], 1)
+    assert (slabs - f).abs().max() < 3e-6
+    (f * gf).sum().add((d * gd).sum()).backward()
+    for mine, ref, what in ((t.grad, gt, 'tex'), (s.grad, gs, 'seg'), (c.grad, gc, 'cam')):
+        assert (mine - ref).abs().max() <= 2e-4 * max(1.0, ref.abs().max().item()), what
+    # head gradients land in the matching blocks of the dense oracle decoder
+    H = 64
+    w1g = gp[0]
+    assert (heads[0][2].grad - w1g[0:H, 0:32]).abs().max() < 2e-4 * max(1.0, w1g.abs().max().item())
+    assert (heads[2][4].grad - gp[2][51:52, 2 * H:]).abs().max() < 2e-4 * max(1.0, gp[2].abs().max().item())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('jitter', ['tensor', 'hash'])
+def test_raymarch_autograd_forward_is_fused_kernel_backward_matches_oracle(jitter):
+    from ide3d_b200 import render
+    tex, seg, dec, cam = _random_case(2, 16, seed=4)
+    g = torch.Generator().manual_seed(1)
+    u = torch.rand(2, RES[0] * RES[1], S, 1, generator=g) if jitter == 'tensor' else None
+    seed = None if jitter == 'tensor' else 0x1234_5678_9ABC_DEF1
+    gf, gd = torch.randn(2, 30, 51, generator=g), torch.randn(2, 30, 1, generator=g)
+    if jitter == 'hash':
+        u_ref = torch.from_numpy(orr.hash_uniform(torch.arange(2 * 30 * S).numpy(), seed)).reshape(2, 30, S, 1)
+    else:
+        u_ref = u
+    rgb, depth, gt, gs, gc, gp = _oracle_grads(tex, seg, dec, cam, u_ref, gf, gd)
+
+    dev = 'cuda'
+    heads = [tuple(h[:2]) + tuple(t.to(dev).requires_grad_(True) for t in h[2:]) for h in three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)]
+    t, s, c = [x.to(dev).requires_grad_(True) for x in (tex, seg, cam)]
+    feat, d, w = render.raymarch(t, s, heads, c, resolution=RES, num_steps=S, jitter_u=None if u is None else u.to(dev), jitter_seed=seed)
+    with torch.no_grad():
+        feat0, d0, _ = render.raymarch(t.detach(), s.detach(), [tuple(h[:2]) + tuple(x.detach() for x in h[2:]) for h in heads], c.detach(),
+                                       resolution=RES, num_steps=S, jitter_u=None if u is None else u.to(dev), jitter_seed=seed)
+    assert torch.equal(feat, feat0) and torch.equal(d, d0) and w is None            # same kernel, same bits
+    assert (feat.cpu() - rgb).abs().max() < 2e-4
+    (feat * gf.to(dev)).sum().add((d * gd.to(dev)).sum()).backward()
+    for mine, ref, what in ((t.grad, gt, 'tex'), (s.grad, gs, 'seg'), (c.grad, gc, 'cam')):
+        assert (mine.cpu() - ref).abs().max() <= 5e-4 * max(1.0, ref.abs().max().item()), what
+    assert (heads[1][3].grad.cpu() - gp[1][64:128]).abs().max() < 5e-4 * max(1.0, gp[1].abs().max().item())
+
+
+@pytest.mark.gpu
+def test_generator_synthesis_is_differentiable_end_to_end():
+    """PTI-style use: gradients of an image loss reach ws, the backbone weights and the decoder heads."""
+    from ide3d_b200.training.triplane import TriPlaneGenerator
+    torch.manual_seed(0)
+    G = TriPlaneGenerator(z_dim=32, w_dim=32, img_resolution=64, plane_resolution=32, render_size=16, channel_base=512, channel_max=16,
+                          sr_channels=(8, 8), mapping_kwargs=dict(num_layers=2)).cuda().train().requires_grad_(True)
+    ws = torch.randn(2, G.num_ws, G.w_dim, device='cuda', requires_grad=True)
+    label = torch.tensor([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 2.7, 0, 0, 0, 1, 4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1.], device='cuda').repeat(2, 1)
+    img = G.synthesis(ws, c=label, noise_mode='const', num_steps=8, perturb=None)
+    img.square().mean().backward()
+    assert ws.grad is not None and torch.isfinite(ws.grad).all() and ws.grad.abs().max() > 0
+    r = G.synthesis.renderer
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in r.parameters())
+    assert r.sigma_net.fc2.weight.grad.abs().max() > 0 and G.synthesis.vb32.conv1.weight.grad.abs().max() > 0
