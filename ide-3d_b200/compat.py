@@ -29,6 +29,11 @@ def install(include_dnnlib=False):
     names = list(_ALIASES) + (['dnnlib', 'dnnlib.util'] if include_dnnlib else [])
     for name in names:
         sys.modules[name] = importlib.import_module(f'{pkg}.{name}')
+    try:                                   # extract_shapes.py:8 imports mrcfile only to write the sigma grid (:191-192)
+        import mrcfile  # noqa: F401
+    except ImportError:
+        sys.modules['mrcfile'] = importlib.import_module(f'{pkg}.mrc')
+        names.append('mrcfile')
     return names
 
 

@@ -382,43 +382,49 @@ __global__ void __launch_bounds__(256) modconv_epilogue_planar_kernel(const EpiA
 }
 
 // channels_last: one 16-byte vector = N consecutive channels of one pixel; scale / bias are vectors, the noise a scalar.
+// Work items are (sample, chunk of 256*UNROLL vectors): the sample index is block-uniform and the position inside the
+// sample fits 32 bits, so the per-vector index math is one shift/mask (power-of-two channel counts) or one 32-bit division
+// -- the first version spent 3/4 of its issue slots on 64-bit div/mod (profiles/r01_ncu_modconv_epilogue.txt).
 template <typename T, int A, int UNROLL>
-__global__ void __launch_bounds__(256) modconv_epilogue_cl_kernel(const EpiArgs p) {
+__global__ void __launch_bounds__(256) modconv_epilogue_cl_kernel(const EpiArgs p, unsigned chunks_per_sample, long long items, int cv_shift) {
     using S = typename Acc<T>::type;
     constexpr int N = Vec<T>::N;
     const S alpha = (S)p.alpha, gain = (S)p.gain, clamp = (S)p.clamp;
-    const long long nvec = p.n * p.hw * p.c / N;
-    const long long stride = (long long)gridDim.x * blockDim.x;
     const unsigned cv = (unsigned)(p.c / N);                     // vectors per pixel
-    for (long long v0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; v0 < nvec; v0 += stride * UNROLL) {
+    const unsigned svec = (unsigned)p.hw * cv;                   // vectors per sample (host guarantees < 2^31)
+    for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+        const unsigned smp = (unsigned)(item / chunks_per_sample);
+        const unsigned chunk = (unsigned)(item - (long long)smp * chunks_per_sample);
+        const long long vbase = (long long)smp * svec;
+        const unsigned v0 = chunk * (256u * UNROLL) + threadIdx.x;
         S vx[UNROLL][N];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u)
-            if (v0 + u * stride < nvec) load_vec((const T*)p.x, v0 + u * stride, vx[u]);
+            if (v0 + u * 256u < svec) load_vec((const T*)p.x, vbase + v0 + u * 256u, vx[u]);
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
-            const long long v = v0 + u * stride;
-            if (v >= nvec) continue;
-            const long long pix = v / cv;
-            const long long c0 = (v - pix * cv);                  // vector index inside the pixel
-            const long long smp = pix / p.hw;
+            const unsigned vi = v0 + u * 256u;
+            if (vi >= svec) continue;
+            unsigned pix, c0;
+            if (cv_shift >= 0) { pix = vi >> cv_shift; c0 = vi & (cv - 1u); }
+            else { pix = vi / cv; c0 = vi - pix * cv; }
             S d[N], bb[N], out[N];
-            if (p.scale) load_vec_keep<T>((const T*)p.scale, smp * cv + c0, d);
+            if (p.scale) load_vec_keep<T>((const T*)p.scale, (long long)smp * cv + c0, d);
             if (p.b) load_vec_keep<T>((const T*)p.b, c0, bb);
-            const S nz = p.noise ? to_acc<T>(__ldg((const T*)p.noise + (p.noise_batch == 1 ? pix - smp * p.hw : pix))) : (S)0;
+            const S nz = p.noise ? to_acc<T>(__ldg((const T*)p.noise + (p.noise_batch == 1 ? (long long)pix : (long long)smp * p.hw + pix))) : (S)0;
 #pragma unroll
             for (int j = 0; j < N; ++j) {
                 S t = p.scale ? vx[u][j] * d[j] : vx[u][j];
                 if (p.noise) t = p.scale ? vx[u][j] * d[j] + nz : vx[u][j] + nz;
                 out[j] = eval<S, A>(t, p.b ? bb[j] : (S)0, (S)0, (S)0, (S)1, 0, alpha, gain, clamp);
             }
-            if (p.y) store_vec((T*)p.y, v, out);
+            if (p.y) store_vec((T*)p.y, vbase + vi, out);
             if (p.y2) {
                 S d2[N];
-                load_vec_keep<T>((const T*)p.scale2, smp * cv + c0, d2);
+                load_vec_keep<T>((const T*)p.scale2, (long long)smp * cv + c0, d2);
 #pragma unroll
                 for (int j = 0; j < N; ++j) out[j] *= d2[j];
-                store_vec((T*)p.y2, v, out);
+                store_vec((T*)p.y2, vbase + vi, out);
             }
         }
     }
@@ -431,10 +437,15 @@ static int launch_epilogue(const EpiArgs& p, int channels_last, cudaStream_t st)
     const long long cap = (long long)sm_count() * 8;
     if (channels_last) {
         if (p.c % N != 0) IDE3D_FAIL(IDE3D_UNSUPPORTED, "modconv_epilogue: channels_last needs C %% %d == 0", N);
-        const long long nvec = p.n * p.hw * p.c / N;
-        long long blocks = ceil_div<long long>(nvec, 256ll * UNROLL);
-        if (blocks > cap) blocks = cap;
-        modconv_epilogue_cl_kernel<T, A, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(p);
+        const long long svec = p.hw * (p.c / N);
+        if (svec >= (1ll << 31)) IDE3D_FAIL(IDE3D_UNSUPPORTED, "modconv_epilogue: more than 2^31 vectors per sample");
+        const long long cps = ceil_div<long long>(svec, 256ll * UNROLL);
+        const long long items = p.n * cps;
+        const long long blocks = items < cap ? items : cap;
+        const long long cvn = p.c / N;
+        int cv_shift = -1;
+        if ((cvn & (cvn - 1)) == 0) { cv_shift = 0; while ((1ll << cv_shift) < cvn) ++cv_shift; }
+        modconv_epilogue_cl_kernel<T, A, UNROLL><<<(unsigned)blocks, 256, 0, st>>>(p, (unsigned)cps, items, cv_shift);
         IDE3D_CHECK_LAUNCH("modconv_epilogue_cl_kernel");
         return IDE3D_OK;
     }

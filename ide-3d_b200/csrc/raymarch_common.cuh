@@ -232,6 +232,86 @@ __device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const Plan
     }
 }
 
+// Per-axis form of the same gather (tcgen05 producers): the three planes share their axes -- x is the column of planes 0 and
+// 2, y the row of plane 0 and the column of plane 1, z the row of planes 1 and 2 -- so the floor / fraction / validity /
+// clamp work is done once per axis role (4 roles) instead of once per tap (12 taps), and a tap's offset and weight are one
+// add and one multiply.  Same arithmetic as gather_chunk_cl: w = (x-weight or 0) * (y-weight or 0), identical products.
+struct AxisFoot {
+    int i0;
+    float f;
+};
+__device__ __forceinline__ AxisFoot axis_foot(float u, int D) {
+    AxisFoot a;
+    const float ix = ((u + 1.f) * (float)D - 1.f) * 0.5f;
+    const float f0 = floorf(ix);
+    a.f = ix - f0;
+    a.i0 = (int)fminf(fmaxf(f0, -2.f), (float)D + 1.f);         // far-away points stay out of range instead of wrapping
+    return a;
+}
+struct AxisTaps {
+    int lo, hi;          // clamped indices, pre-multiplied by the stride of the role (float4 units)
+    float wlo, whi;      // weights, 0 for an out-of-range tap
+};
+__device__ __forceinline__ AxisTaps axis_taps(int i0, float f, int D, int stride) {
+    AxisTaps t;
+    const bool lo_ok = (unsigned)i0 < (unsigned)D, hi_ok = (unsigned)(i0 + 1) < (unsigned)D;
+    t.lo = min(max(i0, 0), D - 1) * stride;
+    t.hi = min(max(i0 + 1, 0), D - 1) * stride;
+    t.wlo = lo_ok ? 1.f - f : 0.f;
+    t.whi = hi_ok ? f : 0.f;
+    return t;
+}
+template <typename Store>
+__device__ __forceinline__ void gather_chunk_axes(const PlaneView& tex, const PlaneView& seg, int n, float cx, float cy,
+                                                  float cz, int lane, Store store) {
+    const int W = tex.w, H = tex.h;
+    const int sh4 = (int)(tex.sh >> 2), sw4 = (int)(tex.sw >> 2);      // strides in float4 units (multiples of 4 floats)
+    const AxisFoot ax = axis_foot(cx, W), ayr = axis_foot(cy, H), ayc = axis_foot(cy, W), az = axis_foot(cz, H);
+    const int q = lane & 7, grp = lane >> 3;
+    const float4* tb = reinterpret_cast<const float4*>(tex.base + (long long)n * tex.sn) + q;
+    const float4* sb = reinterpret_cast<const float4*>(seg.base + (long long)n * seg.sn) + q;
+
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        const int src = it * 4 + grp;
+        const AxisTaps X = axis_taps(__shfl_sync(kFull, ax.i0, src), __shfl_sync(kFull, ax.f, src), W, sw4);     // column of planes 0, 2
+        const AxisTaps Yr = axis_taps(__shfl_sync(kFull, ayr.i0, src), __shfl_sync(kFull, ayr.f, src), H, sh4);  // row of plane 0
+        const AxisTaps Yc = axis_taps(__shfl_sync(kFull, ayc.i0, src), __shfl_sync(kFull, ayc.f, src), W, sw4);  // column of plane 1
+        const AxisTaps Z = axis_taps(__shfl_sync(kFull, az.i0, src), __shfl_sync(kFull, az.f, src), H, sh4);     // row of planes 1, 2
+        // tap order inside a plane as in gather_chunk_cl: (col lo,row lo) (col hi,row lo) (col lo,row hi) (col hi,row hi)
+        float4 v[12], u[12];
+#define IDE3D_PLANE_LOADS(k, C, R)                                                                                 \
+        {                                                                                                         \
+            const int o0 = R.lo + C.lo + k * (kFeat / 4), o1 = R.lo + C.hi + k * (kFeat / 4);                     \
+            const int o2 = R.hi + C.lo + k * (kFeat / 4), o3 = R.hi + C.hi + k * (kFeat / 4);                     \
+            v[4 * k + 0] = __ldg(tb + o0); v[4 * k + 1] = __ldg(tb + o1); v[4 * k + 2] = __ldg(tb + o2); v[4 * k + 3] = __ldg(tb + o3); \
+            u[4 * k + 0] = __ldg(sb + o0); u[4 * k + 1] = __ldg(sb + o1); u[4 * k + 2] = __ldg(sb + o2); u[4 * k + 3] = __ldg(sb + o3); \
+        }
+        IDE3D_PLANE_LOADS(0, X, Yr)
+        IDE3D_PLANE_LOADS(1, Yc, Z)
+        IDE3D_PLANE_LOADS(2, X, Z)                                       // all 24 LDG.128 in flight
+#undef IDE3D_PLANE_LOADS
+        float at[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
+#define IDE3D_PLANE_BLEND(k, C, R)                                                                                 \
+        {                                                                                                         \
+            const float w4[4] = {C.wlo * R.wlo, C.whi * R.wlo, C.wlo * R.whi, C.whi * R.whi};                     \
+            float p[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};                                       \
+            _Pragma("unroll") for (int tap = 0; tap < 4; ++tap) {                                                 \
+                const float4 a = v[k * 4 + tap], b = u[k * 4 + tap];                                              \
+                const float w_ = w4[tap];                                                                         \
+                p[0] += a.x * w_; p[1] += a.y * w_; p[2] += a.z * w_; p[3] += a.w * w_;                           \
+                r[0] += b.x * w_; r[1] += b.y * w_; r[2] += b.z * w_; r[3] += b.w * w_;                           \
+            }                                                                                                     \
+            _Pragma("unroll") for (int j = 0; j < 4; ++j) { at[j] += p[j]; as[j] += r[j]; }                       \
+        }
+        IDE3D_PLANE_BLEND(0, X, Yr)
+        IDE3D_PLANE_BLEND(1, Yc, Z)
+        IDE3D_PLANE_BLEND(2, X, Z)
+#undef IDE3D_PLANE_BLEND
+        store(src, q, at, as);
+    }
+}
+
 // staging-row flavour used by the SIMT kernels: stage[s*kRow + 0..31] = texture, [32..63] = shape features
 template <bool kChannelsLast>
 __device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneView& seg, int n, float cx,

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
                 }
                 unsigned char* a_hi = smem + kSmStage + stage * 2 * kTileBytes;
                 unsigned char* a_lo = a_hi + kTileBytes;
-                if (a.debug != 1) gather_chunk_cl<true>(a.tex, a.seg, r.n, cx, cy, cz, lane,
+                if (a.debug != 1) gather_chunk_axes(a.tex, a.seg, r.n, cx, cy, cz, lane,
                                       [&](int src, int qq, const float (&at)[4], const float (&as)[4]) {
                                           const int row = quarter * 32 + src;
                                           __nv_bfloat16 h[4], l[4];

@@ -586,15 +586,19 @@ __global__ void __launch_bounds__(256) upfirdn2d_cl_patch_kernel(const UpfirArgs
     const unsigned cvn = (unsigned)(p.in_c >> 2);
     const long long total = (long long)patches_x * patches_y * p.in_n * cvn;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long r0 = i / cvn;
-        const int cv = (int)(i - r0 * cvn);
-        const int pxi = (int)(r0 % patches_x);
-        const long long r1 = r0 / patches_x;
-        const int pyi = (int)(r1 % patches_y);
-        const int n = (int)(r1 / patches_y);
+        int cv, pxi, pyi, n;
+        if (total <= 0xffffffffll) {                             // 32-bit index math (64-bit div/mod costs ~60 instructions each)
+            const unsigned ii = (unsigned)i, r0 = ii / cvn, r1 = r0 / (unsigned)patches_x;
+            cv = (int)(ii - r0 * cvn); pxi = (int)(r0 - r1 * (unsigned)patches_x);
+            n = (int)(r1 / (unsigned)patches_y); pyi = (int)(r1 - (unsigned)n * (unsigned)patches_y);
+        } else {
+            const long long r0 = i / cvn, r1 = r0 / patches_x;
+            cv = (int)(i - r0 * cvn); pxi = (int)(r0 % patches_x);
+            pyi = (int)(r1 % patches_y); n = (int)(r1 / patches_y);
+        }
         const int ox0 = pxi * kPatch, oy0 = pyi * kPatch;
         const int ix0 = ox0 * DX / UX - ax + AX::lo(), iy0 = oy0 * DY / UY - ay + AY::lo();
-        const T* xin = (const T*)p.x + n * p.isn + cv * 4;
+        const T* xin = (const T*)p.x + (long long)n * p.isn + cv * 4;
         cl_patch_body<T, UX, UY, DX, DY, FW, FH, PHX, PHY, kEpi>(p, fk, n, cv, ox0, oy0, [&](int r, int q, float (&w)[4]) {
             const int gy = iy0 + r, gx = ix0 + q;
             if ((unsigned)gy < (unsigned)p.in_h && (unsigned)gx < (unsigned)p.in_w) V4<T>::ld(xin + gy * p.ish + gx * p.isw, w);

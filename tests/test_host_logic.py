@@ -2,6 +2,7 @@
 (oracle.backend.cpu_reference_ops) -- API contract reconstructed from the reference's call sites."""
 
 import math
+import os
 import sys
 
 import numpy as np
@@ -150,3 +151,22 @@ def test_setup_filter_matches_oracle():
     from oracle import ops as oops
     for taps, kw in (([1, 3, 3, 1], {}), ([1, 2, 1], dict(gain=4)), (list(range(1, 13)), {}), ([[1, 2], [3, 4]], dict(flip_filter=True)), (None, {})):
         assert torch.equal(up.setup_filter(taps, **kw), oops.setup_filter(taps, **kw))
+
+
+def test_mrc_writer_round_trip_and_mrcfile_shim(tmp_path):
+    """extract_shapes.py:191-192 writes the sigma grid as a mode-2 MRC volume; ide3d_b200.mrc does it without `mrcfile`."""
+    from ide3d_b200 import mrc
+    vol = np.random.RandomState(0).randn(5, 7, 9).astype(np.float32)
+    path = str(tmp_path / 'grid.mrc')
+    with mrc.new_mmap(path, overwrite=True, shape=vol.shape, mrc_mode=2) as m:          # the reference's exact call shape
+        m.data[:] = vol
+    assert os.path.getsize(path) == 1024 + vol.size * 4
+    back, hdr = mrc.read_mrc(path)
+    assert np.array_equal(back, vol) and (hdr['nx'], hdr['ny'], hdr['nz'], hdr['mode']) == (9, 7, 5, 2)
+    assert hdr['nversion'] == 20140 and abs(hdr['dmean'] - vol.mean()) < 1e-6 and hdr['dmax'] == vol.max()
+    with pytest.raises(ValueError):
+        with mrc.new_mmap(path, shape=vol.shape):
+            pass
+    mrc.write_mrc(path, torch.from_numpy(vol).double(), voxel_size=0.5)
+    back2, hdr2 = mrc.read_mrc(path)
+    assert np.array_equal(back2, vol) and hdr2['cella'] == (4.5, 3.5, 2.5)

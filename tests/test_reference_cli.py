@@ -4,7 +4,8 @@ imported unmodified from /root/reference) run against this package through `comp
 What is stubbed, and why it does not touch the contract under test:
   * `legacy.load_network_pkl`  -> returns a small random-init TriPlaneGenerator (no checkpoint pickle exists offline)
   * `dnnlib.util.open_url`     -> dummy context manager (the "pickle path" is never read)
-  * imageio / mrcfile / plyfile / skimage -> absent output-writer dependencies of the scripts
+  * imageio / plyfile / skimage -> absent output-writer dependencies of the scripts; `mrcfile` is supplied by
+    compat.install() (ide3d_b200.mrc, a numpy MRC2014 writer)
   * torch.device('cuda') inside the scripts -> 'cpu', and the CUDA entry points -> oracle (no GPU in this container)
   * torchvision's save_image   -> recorder (the scripts call it with the removed `range=` keyword)
 Skipped on machines without /root/reference (the GPU box)."""
@@ -32,7 +33,7 @@ def ref_env(monkeypatch):
     saved = dict(sys.modules)
     monkeypatch.syspath_prepend(REF)
     monkeypatch.setattr(sys, 'dont_write_bytecode', True)
-    for name in ('imageio', 'mrcfile', 'plyfile', 'skimage', 'skimage.measure'):
+    for name in ('imageio', 'plyfile', 'skimage', 'skimage.measure'):      # mrcfile: compat.install() supplies ide3d_b200.mrc
         monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
     sys.modules['skimage'].measure = sys.modules['skimage.measure']
     compat.install()                                     # training.*, torch_utils.* -> this package
@@ -54,7 +55,7 @@ def ref_env(monkeypatch):
 
     with cpu_reference_ops():
         yield G, _Dev()
-    ours = {'training', 'torch_utils', 'dnnlib', 'legacy', 'gen_images', 'gen_videos', 'extract_shapes', 'camera_utils'}
+    ours = {'training', 'torch_utils', 'dnnlib', 'legacy', 'gen_images', 'gen_videos', 'extract_shapes', 'camera_utils', 'mrcfile'}
     for k in list(sys.modules):                          # drop only what this fixture introduced (cv2 & co. cannot re-import)
         if k not in saved and k.split('.')[0] in ours:
             del sys.modules[k]
@@ -106,3 +107,17 @@ def test_gen_videos_frame_loop_runs_unchanged(ref_env, monkeypatch):
                         image_mode='image_seg', device=torch.device('cpu'))
     assert len(frames) == 4                                                      # 2 keyframes x 2 frames
     assert frames[0].dtype == np.uint8 and frames[0].shape == (64, 128, 3)       # image | colourised mask, side by side
+
+
+def test_extract_shapes_main_writes_mrc_through_the_shim(ref_env, tmp_path, monkeypatch):
+    """The script's __main__ block end to end on CPU: argparse -> load (stubbed pickle) -> block walk -> sample_voxel chunks ->
+    `mrcfile.new_mmap(...)` (ide3d_b200.mrc via compat.install) + np.save; the .mrc holds the same grid as the .npy."""
+    import runpy
+    from ide3d_b200 import mrc
+    out = tmp_path / 'shapes'
+    monkeypatch.setattr(sys, 'argv', ['extract_shapes.py', '--network', 'unused.pkl', '--seeds', '0', '--voxel_resolution', '10',
+                                      '--cube_size', '1.0', '--outdir', str(out)])
+    runpy.run_path(os.path.join(REF, 'extract_shapes.py'), run_name='__main__')
+    grid = np.load(out / '0.npy')
+    vol, hdr = mrc.read_mrc(str(out / '0.mrc'))
+    assert grid.shape == (10, 10, 10) and np.array_equal(vol, grid.astype(np.float32)) and hdr['mode'] == 2
