@@ -114,6 +114,7 @@ def get_lib():
     lib.ide3d_initial_rays.argtypes = [i32, i32, f32, i32, i32, f32, f32, vp, vp, vp, vp]
     lib.ide3d_transform_points.argtypes = [vp, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]
     lib.ide3d_sample_triplane.argtypes = [C.POINTER(TriPlane), vp, i64, vp, vp]
+    lib.ide3d_mask2color.argtypes = [vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, vp, i32, vp]
     lib.ide3d_integrate.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp]
     lib.ide3d_sample_pdf.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp]
     for name in ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_act', 'raymarch_fwd', 'sample_voxel',
@@ -132,7 +133,7 @@ def exported_symbols():
             'ide3d_upfirdn2d', 'ide3d_upfirdn2d_add', 'ide3d_upfirdn2d_epilogue',
             'ide3d_filtered_lrelu', 'ide3d_filtered_lrelu_act', 'ide3d_raymarch_fwd', 'ide3d_sample_voxel',
             'ide3d_sigma_grid', 'ide3d_planes_to_nhwc', 'ide3d_initial_rays', 'ide3d_transform_points',
-            'ide3d_sample_triplane', 'ide3d_integrate', 'ide3d_sample_pdf']
+            'ide3d_sample_triplane', 'ide3d_integrate', 'ide3d_sample_pdf', 'ide3d_mask2color']
 
 
 def check(rc, allow_unsupported=False):

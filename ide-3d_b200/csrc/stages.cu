@@ -304,3 +304,43 @@ extern "C" int ide3d_sample_pdf(const float* bins, const float* weights, const f
     IDE3D_CHECK_LAUNCH("pdf_kernel");
     return IDE3D_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------------
+// mask2color (dnnlib/seg_tools.py:75-82): argmax over the class logits + colour look-up, one thread per pixel.
+namespace ide3d {
+template <typename O>
+__global__ void __launch_bounds__(256) mask2color_kernel(const float* __restrict__ m, int c, int h, int w, long long sn, long long sc,
+                                                         long long sh, long long sw, const float* __restrict__ lut, O* __restrict__ out,
+                                                         long long total) {
+    const long long hw = (long long)h * w;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long n = i / hw, r = i - n * hw;
+        const int y = (int)(r / w), x = (int)(r - (long long)y * w);
+        const float* p = m + n * sn + y * sh + x * sw;
+        float best = p[0];
+        int arg = 0;
+        for (int k = 1; k < c; ++k) {
+            const float v = p[k * sc];
+            if (v > best || (v != v && best == best)) { best = v; arg = k; }      // first maximum; NaN counts as maximal (torch.argmax)
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) out[(n * 3 + j) * hw + r] = (O)lut[arg * 3 + j];
+    }
+}
+}  // namespace ide3d
+
+extern "C" int ide3d_mask2color(const float* masks, int n, int c, int h, int w, int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                                int64_t stride_w, const float* lut, void* out, int out_u8, ide3d_stream_t stream) {
+    IDE3D_REQUIRE(n >= 0 && c >= 1 && h >= 0 && w >= 0, "mask2color: bad sizes");
+    const long long total = (long long)n * h * w;
+    if (total == 0) return IDE3D_OK;
+    IDE3D_REQUIRE(masks && lut && out, "mask2color: null tensor");
+    long long grid = ide3d::ceil_div<long long>(total, 256);
+    const long long cap = (long long)ide3d::sm_count() * 16;
+    if (grid > cap) grid = cap;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (out_u8) ide3d::mask2color_kernel<unsigned char><<<(unsigned)grid, 256, 0, st>>>(masks, c, h, w, stride_n, stride_c, stride_h, stride_w, lut, (unsigned char*)out, total);
+    else ide3d::mask2color_kernel<float><<<(unsigned)grid, 256, 0, st>>>(masks, c, h, w, stride_n, stride_c, stride_h, stride_w, lut, (float*)out, total);
+    IDE3D_CHECK_LAUNCH("mask2color_kernel");
+    return IDE3D_OK;
+}

@@ -16,6 +16,7 @@
  *   ide3d_sample_triplane     dnnlib/util.py:580                    sample_from_triplane
  *   ide3d_integrate           training/volumetric_rendering.py:34   fancy_integration
  *   ide3d_sample_pdf          training/volumetric_rendering.py:224  sample_pdf
+ *   ide3d_mask2color          dnnlib/seg_tools.py:75                mask2color
  *   ide3d_sample_voxel        generator.synthesis.renderer.sample_voxel (call site extract_shapes.py:146)
  *   ide3d_sigma_grid          extract_shapes.py:99-150 (create_samples :74-96 + the sample_voxel loop :144-148)
  *   ide3d_raymarch_fwd        the per-frame chain the generator class runs: rays -> jitter -> world
@@ -283,6 +284,13 @@ int ide3d_integrate(const float* rgb_sigma, const float* rays_d_cam, const float
 /* sample_pdf: bins [R, S+1], weights [R, S], u [R, n_imp] -> samples [R, n_imp]. */
 int ide3d_sample_pdf(const float* bins, const float* weights, const float* u, int num_rays, int num_bins,
                      int n_importance, float eps, float* samples, ide3d_stream_t stream);
+
+/* mask2color (dnnlib/seg_tools.py:75-82): per pixel argmax over the c semantic logits (first maximum wins, like
+ * torch.argmax) and colour look-up, one pass.  masks [n, c, h, w] float32 with element strides; lut [c, 3] float32 (the
+ * COLOR_MAP rows, seg_tools.py:13-32); out [n, 3, h, w] float32 dense NCHW -- or, with out_u8 != 0, uint8 (the
+ * `.to(torch.uint8)` that follows in gen_videos.py:24-38 folded in). */
+int ide3d_mask2color(const float* masks, int n, int c, int h, int w, int64_t stride_n, int64_t stride_c, int64_t stride_h,
+                     int64_t stride_w, const float* lut, void* out, int out_u8, ide3d_stream_t stream);
 
 #ifdef __cplusplus
 }

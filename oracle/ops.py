@@ -230,3 +230,12 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     if down > 1:
         t = upfirdn2d(t, f, down=down, flip_filter=flip_filter)
     return t
+
+
+def mask2color(masks, color_map):
+    """dnnlib/seg_tools.py:75-82: argmax over dim 1, colour per class (classes without an entry stay 0)."""
+    idx = torch.argmax(masks, dim=1).float()
+    out = torch.zeros((idx.shape[0], idx.shape[1], idx.shape[2], 3), dtype=torch.float)
+    for key, col in color_map.items():
+        out[idx == key] = torch.tensor(col, dtype=torch.float)
+    return out.permute(0, 3, 1, 2)

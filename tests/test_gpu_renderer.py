@@ -297,3 +297,20 @@ def test_camera_helpers_golden():
         assert_close(vr.create_cam2world_matrix(-o, o, device=DEV), g[f'c2w{i}'], 2e-6)
         la = vr.LookAtPoseSampler.sample(float(h), float(v), torch.tensor([0, 0, 0.2], device=DEV), radius=2.7, device=DEV)
         assert_close(la, g[f'lookat{i}'], 2e-6)
+
+
+def test_mask2color_matches_reference_loop():
+    """dnnlib/seg_tools.py:75-82 (argmax + 19 masked assignments) vs the one-pass kernel; ties -> first maximum; strided input."""
+    from ide3d_b200.dnnlib import seg_tools
+    from oracle import ops as oops
+    g = torch.Generator().manual_seed(2)
+    m = torch.randn(3, 19, 21, 17, generator=g)
+    m[0, 4, 3, 3] = m[0, 9, 3, 3] = 50.0                                  # tie: argmax returns the first
+    want = oops.mask2color(m, seg_tools.COLOR_MAP)
+    got = seg_tools.mask2color(m.to(DEV))
+    assert got.dtype == torch.float32 and torch.equal(got.cpu(), want)
+    got8 = seg_tools.mask2color(m.to(DEV).contiguous(memory_format=torch.channels_last), to_uint8=True)
+    assert got8.dtype == torch.uint8 and torch.equal(got8.cpu(), want.to(torch.uint8))
+    wide = torch.randn(2, 51, 8, 8, generator=g).to(DEV)                   # the renderer's feat layout: logits are channels 32..50
+    sl = wide[:, 32:51]
+    assert torch.equal(seg_tools.mask2color(sl).cpu(), oops.mask2color(sl.cpu(), seg_tools.COLOR_MAP))
