@@ -93,7 +93,9 @@ __device__ __forceinline__ Foot footprint(float u, float v, int W, int H) {
 // (cx,cy,cz): this lane's own sample in plane grid units.  Inactive lanes pass any finite value.
 // `store(sample, q, at, as)` receives, for sample `sample` (0..31 of the chunk), the texture / shape features of
 // channels 4q..4q+3.
-template <bool kChannelsLast, typename Store>
+// kSkipTex: the caller only needs the shape features (sigma-only queries of a decoder whose sigma head reads the shape
+// planes alone): the texture tri-plane is not touched at all.
+template <bool kChannelsLast, bool kSkipTex = false, typename Store>
 __device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const PlaneView& seg, int n, float cx,
                                                 float cy, float cz, int lane, Store store) {
     const int W = tex.w, H = tex.h;
@@ -129,17 +131,19 @@ __device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const Plan
                     if (kChannelsLast) {
                         const long long to = (long long)yy * tex.sh + (long long)xx * tex.sw + k * kFeat + q * 4;
                         const long long so = (long long)yy * seg.sh + (long long)xx * seg.sw + k * kFeat + q * 4;
-                        const float4 a = __ldg(reinterpret_cast<const float4*>(tbase + to));
                         const float4 b = __ldg(reinterpret_cast<const float4*>(sbase + so));
-                        pt[0] += a.x * wgt; pt[1] += a.y * wgt; pt[2] += a.z * wgt; pt[3] += a.w * wgt;
                         ps[0] += b.x * wgt; ps[1] += b.y * wgt; ps[2] += b.z * wgt; ps[3] += b.w * wgt;
+                        if constexpr (!kSkipTex) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(tbase + to));
+                            pt[0] += a.x * wgt; pt[1] += a.y * wgt; pt[2] += a.z * wgt; pt[3] += a.w * wgt;
+                        }
                     } else {
                         const long long to = (long long)yy * tex.sh + (long long)xx * tex.sw;
                         const long long so = (long long)yy * seg.sh + (long long)xx * seg.sw;
 #pragma unroll
                         for (int j = 0; j < 4; ++j) {
                             const int c = k * kFeat + q * 4 + j;
-                            pt[j] += __ldg(tbase + to + (long long)c * tex.sc) * wgt;
+                            if constexpr (!kSkipTex) pt[j] += __ldg(tbase + to + (long long)c * tex.sc) * wgt;
                             ps[j] += __ldg(sbase + so + (long long)c * seg.sc) * wgt;
                         }
                     }
@@ -313,12 +317,12 @@ __device__ __forceinline__ void gather_chunk_axes(const PlaneView& tex, const Pl
 }
 
 // staging-row flavour used by the SIMT kernels: stage[s*kRow + 0..31] = texture, [32..63] = shape features
-template <bool kChannelsLast>
+template <bool kChannelsLast, bool kSkipTex = false>
 __device__ __forceinline__ void gather_chunk(const PlaneView& tex, const PlaneView& seg, int n, float cx,
                                              float cy, float cz, float* __restrict__ stage, int lane) {
-    gather_chunk_to<kChannelsLast>(tex, seg, n, cx, cy, cz, lane, [stage](int src, int q, const float (&at)[4], const float (&as)[4]) {
+    gather_chunk_to<kChannelsLast, kSkipTex>(tex, seg, n, cx, cy, cz, lane, [stage](int src, int q, const float (&at)[4], const float (&as)[4]) {
         float* row = stage + src * kRow;
-        *reinterpret_cast<float4*>(row + q * 4) = make_float4(at[0], at[1], at[2], at[3]);
+        if constexpr (!kSkipTex) *reinterpret_cast<float4*>(row + q * 4) = make_float4(at[0], at[1], at[2], at[3]);
         *reinterpret_cast<float4*>(row + kFeat + q * 4) = make_float4(as[0], as[1], as[2], as[3]);
     });
     __syncwarp();

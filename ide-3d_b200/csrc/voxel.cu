@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(kVBlock, 1) voxel_kernel(const VoxelArgs a) {
             }
             x *= a.box_scale; y *= a.box_scale; z *= a.box_scale;
         }
-        gather_chunk<kChannelsLast>(a.tex, a.seg, n, x, y, z, stage, lane);
+        // sigma of the three-head decoder reads the shape planes only: skip the texture tri-plane (half of the gather)
+        if (KIND == kThreeHead64 && a.sigma_only) gather_chunk<kChannelsLast, true>(a.tex, a.seg, n, x, y, z, stage, lane);
+        else gather_chunk<kChannelsLast>(a.tex, a.seg, n, x, y, z, stage, lane);
         const float* row = stage + lane * kRow;
         if (a.sigma_only) {
             const float sg = decode_sigma<KIND>(row, wsm);

@@ -3,3 +3,4 @@ set -x
 timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench_cl.json | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['kernel_ms'])"
+timeout 300 python scripts/bench_voxel.py 2>&1 | tail -4 | cut -c1-300
