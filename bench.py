@@ -42,7 +42,7 @@ RENDER = 64
 PLANE = 256
 FRAME_ALGO_BYTES = 2 * 96 * PLANE * PLANE * 4 + RENDER * RENDER * (32 + 19 + 1 + 1) * 4   # 51.20 MB
 METRIC = 'rendered frames/sec at 64^2 neural x 96 samples -> 512^2'
-RAYMARCH_DRAM_BYTES_NCU = 329945344      # 320.16 MB read + 9.79 MB written per 8-frame launch (part of the planes is still L2-resident from the producer)
+RAYMARCH_DRAM_BYTES_NCU = 333248768      # 320.16 MB read + 9.79 MB written per 8-frame launch (part of the planes is still L2-resident from the producer)
 
 
 def make_labels(n):
@@ -314,10 +314,10 @@ def main():
                     'd2h_bytes_per_step': int(BATCH * world * 3 * 512 * 512), 'call': 'ide3d_b200.dist.stream_frames_sharded (pinned host ws/c -> uint8 frames in pinned host memory; D2H of batch i overlaps batch i+1)'},
             'gpu_launches': int(launches),
             'roofline': {'kernel': 'raymarch_tc_kernel (fused gather + tcgen05 decoder MLP + compositing)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': RAYMARCH_DRAM_BYTES_NCU, 'traffic_source': 'profiles/r01_ncu_raymarch_tc.txt (dram__bytes_read+write, one ncu --set full capture of this launch)', 'peak_source': peak_src, 'kernel_ms': kern_ms,
+                         'frac': achieved / peak, 'traffic': RAYMARCH_DRAM_BYTES_NCU, 'traffic_source': 'profiles/r01_ncu_raymarch_tc_v2.txt (dram__bytes_read+write, one ncu --set full capture of this launch)', 'peak_source': peak_src, 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': BATCH * FRAME_ALGO_BYTES,
                          'kernel_only_fps': BATCH / (kern_ms * 1e-3), 'renderer_fps_incl_layout_pass': BATCH / (renderer_ms * 1e-3),
-                         'note': 'HBM is not the limiter of this kernel: 24 texel lines per sample are served by L1/L2 and the kernel is issue/XU bound (profiles/r01_ncu_raymarch_tc.txt); frac is reported as the contract asks'},
+                         'note': 'HBM is not the limiter of this kernel: 24 texel lines per sample are served by L1/L2 and the kernel is issue/XU bound (profiles/r01_ncu_raymarch_tc_v2.txt); frac is reported as the contract asks'},
             'clocks': clocks.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
