@@ -42,7 +42,7 @@ RENDER = 64
 PLANE = 256
 FRAME_ALGO_BYTES = 2 * 96 * PLANE * PLANE * 4 + RENDER * RENDER * (32 + 19 + 1 + 1) * 4   # 51.20 MB
 METRIC = 'rendered frames/sec at 64^2 neural x 96 samples -> 512^2'
-RAYMARCH_DRAM_BYTES_NCU = 333248768      # 320.16 MB read + 9.79 MB written per 8-frame launch (part of the planes is still L2-resident from the producer)
+RAYMARCH_DRAM_BYTES_NCU = 333248768      # 321.38 MB read + 11.87 MB written per 8-frame launch (part of the planes is still L2-resident from the producer)
 
 
 def make_labels(n):
