@@ -27,6 +27,22 @@ FUSED_MODCONV_MIN_RES = 1 << 30      # block resolutions >= this use the grouped
 # the reference's NCHW fp32 layout (same values).
 CHANNELS_LAST = os.environ.get('IDE3D_CHANNELS_LAST', '1') != '0'
 CHAIN_MODULATION = True              # epilogues also write the next layer's `x * styles` (SynthesisBlock._features)
+# 1x1 convolutions of NHWC activations as one [N*H*W, I] x [I, O] matrix product (cuBLASLt, tf32 exactly when the cuDNN convolution
+# it replaces would use tf32) instead of cuDNN's conv3d_fprop kernels, which stream these shapes at ~40 % of the HBM peak.
+CONV1X1_AS_MATMUL = os.environ.get('IDE3D_CONV1X1_MM', '0') != '0'
+
+
+def _conv1x1_nhwc(x, weight):
+    """x [N,I,H,W] channels_last dense, weight [O,I,1,1] -> [N,O,H,W] channels_last (a view of the [N*H*W, O] product)."""
+    n, c, h, w = x.shape
+    o = weight.shape[0]
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = bool(torch.backends.cudnn.allow_tf32)
+    try:
+        y = x.permute(0, 2, 3, 1).reshape(n * h * w, c) @ weight.reshape(o, c).t()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    return y.reshape(n, h, w, o).permute(0, 3, 1, 2)
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):
@@ -66,8 +82,13 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
             e.update(scale=dcoefs if demodulate else None, noise=noise)
             return conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
                                                    padding=padding, flip_weight=flip_weight, fir_epilogue=e)
-        x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
-                                            padding=padding, flip_weight=flip_weight)
+        if (CONV1X1_AS_MATMUL and kh == 1 and kw == 1 and up == 1 and down == 1 and padding == 0 and x.dtype == torch.float32 and x.is_cuda
+                and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
+                and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))):
+            x = _conv1x1_nhwc(x, weight)
+        else:
+            x = conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
+                                                padding=padding, flip_weight=flip_weight)
         if epilogue is not None:
             return bias_act.scaled_bias_act(x, scale=dcoefs if demodulate else None, noise=noise, **epilogue)
         if demodulate and noise is not None:

@@ -1,0 +1,58 @@
+"""GPU parity of the WHOLE synthesis path: TriPlaneGenerator.synthesis on cuda (NHWC backbone, chained epilogues, TMA FIR,
+fused skip step, tcgen05 / fp32 ray-march, SR blocks) against the same module evaluated by the CPU oracle in the reference's
+layout (oracle.backend.cpu_reference_ops: NCHW, reference op chain).  cuDNN tf32 is switched off for the comparison so that
+the convolutions are fp32 on both sides; tolerance 5e-3 x max|image| on the 128^2 images (accumulated fp32 rounding through ~20 convolutions
++ the stated ray-march tolerance), 1e-3 on the 32^2 feature image, 2 uint8 levels on the final frames."""
+
+import pytest
+import torch
+
+from oracle.backend import cpu_reference_ops
+
+pytestmark = pytest.mark.gpu
+LABEL = [1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 2.7, 0, 0, 0, 1, 4.2647, 0, 0.5, 0, 4.2647, 0.5, 0, 0, 1]
+
+
+@pytest.fixture(scope='module')
+def case():
+    from ide3d_b200.training.triplane import TriPlaneGenerator
+    torch.manual_seed(0)
+    G = TriPlaneGenerator(z_dim=32, w_dim=32, img_resolution=128, plane_resolution=64, render_size=32, channel_base=2048, channel_max=64,
+                          sr_channels=(32, 32), mapping_kwargs=dict(num_layers=2)).eval().requires_grad_(False)
+    for name, p in G.named_parameters():                        # non-trivial noise so that the noise path is exercised
+        if name.endswith('noise_strength'):
+            p.data.fill_(0.1)
+    z = torch.randn(2, G.z_dim, generator=torch.Generator().manual_seed(5))
+    c = torch.tensor(LABEL).repeat(2, 1)
+    c[1, 3] = 0.15                                              # second camera slightly off-axis
+    kw = dict(noise_mode='const', num_steps=24, perturb=None)
+    with torch.no_grad(), cpu_reference_ops():
+        ws = G.mapping(z, c, truncation_psi=0.7)
+        ref = G.synthesis(ws, c=c, return_dict=True, **kw)
+    return G, ws, c, kw, ref
+
+
+@pytest.mark.parametrize('channels_last,chain,mm', [(True, True, False), (True, True, True), (False, True, False), (True, False, False)])
+def test_synthesis_on_gpu_matches_cpu_oracle(case, channels_last, chain, mm):
+    from ide3d_b200.training import networks as nw
+    G, ws, c, kw, ref = case
+    Gd = G.cuda()
+    saved = (nw.CHANNELS_LAST, nw.CHAIN_MODULATION, nw.CONV1X1_AS_MATMUL, torch.backends.cudnn.allow_tf32)
+    try:
+        nw.CHANNELS_LAST, nw.CHAIN_MODULATION, nw.CONV1X1_AS_MATMUL = channels_last, chain, mm
+        torch.backends.cudnn.allow_tf32 = False
+        with torch.no_grad():
+            out = Gd.synthesis(ws.cuda(), c=c.cuda(), return_dict=True, **kw)
+    finally:
+        nw.CHANNELS_LAST, nw.CHAIN_MODULATION, nw.CONV1X1_AS_MATMUL, torch.backends.cudnn.allow_tf32 = saved
+        G.cpu()
+    report = {}
+    for key, tol in (('image_raw', 1e-3), ('image_depth', 3e-4), ('image', 5e-3), ('image_seg', 5e-3)):
+        a, b = out[key].float().cpu(), ref[key].float()
+        scale = max(1.0, b.abs().max().item())
+        report[key] = ((a - b).abs().max().item(), scale, tol)
+    print('synthesis parity (max abs err, scale, tol):', report)
+    for key, (err, scale, tol) in report.items():
+        assert err <= tol * scale, (key, report)
+    to8 = lambda t: (t * 127.5 + 128).clamp(0, 255).to(torch.uint8).int()
+    assert (to8(out['image'].float().cpu()) - to8(ref['image'])).abs().max() <= 2
