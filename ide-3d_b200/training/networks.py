@@ -29,6 +29,7 @@ CHANNELS_LAST = os.environ.get('IDE3D_CHANNELS_LAST', '1') != '0'
 CHAIN_MODULATION = True              # epilogues also write the next layer's `x * styles` (SynthesisBlock._features)
 # 1x1 convolutions of NHWC activations as one [N*H*W, I] x [I, O] matrix product (cuBLASLt, tf32 exactly when the cuDNN convolution
 # it replaces would use tf32) instead of cuDNN's conv3d_fprop kernels, which stream these shapes at ~40 % of the HBM peak.
+# Measured on B200 (round 1): the step gets SLOWER with it (7.76 vs 7.35 ms), so it stays off; kept as a switch for the record.
 CONV1X1_AS_MATMUL = os.environ.get('IDE3D_CONV1X1_MM', '0') != '0'
 
 

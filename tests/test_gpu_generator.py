@@ -1,8 +1,10 @@
 """GPU parity of the WHOLE synthesis path: TriPlaneGenerator.synthesis on cuda (NHWC backbone, chained epilogues, TMA FIR,
 fused skip step, tcgen05 / fp32 ray-march, SR blocks) against the same module evaluated by the CPU oracle in the reference's
 layout (oracle.backend.cpu_reference_ops: NCHW, reference op chain).  cuDNN tf32 is switched off for the comparison so that
-the convolutions are fp32 on both sides; tolerance 5e-3 x max|image| on the 128^2 images (accumulated fp32 rounding through ~20 convolutions
-+ the stated ray-march tolerance), 1e-3 on the 32^2 feature image, 2 uint8 levels on the final frames."""
+the convolutions are fp32 on both sides.  Tolerances are relative to max|tensor| (2.5 ... 5.9 here): 1e-4 on the 128^2 image and
+semantic maps and on the 32^2 feature image, 2e-5 on depth, 1 uint8 level on the final frames.  Measured on B200 (round 1): image
+4.6e-5 absolute on a 5.9 range, feature image 2.2e-5, depth 2.9e-6, semantic maps 3.0e-5 -- identical for NHWC / NCHW, chained / unchained
+epilogues and the optional matmul form of the 1x1 convolutions."""
 
 import pytest
 import torch
@@ -47,7 +49,7 @@ def test_synthesis_on_gpu_matches_cpu_oracle(case, channels_last, chain, mm):
         nw.CHANNELS_LAST, nw.CHAIN_MODULATION, nw.CONV1X1_AS_MATMUL, torch.backends.cudnn.allow_tf32 = saved
         G.cpu()
     report = {}
-    for key, tol in (('image_raw', 1e-3), ('image_depth', 3e-4), ('image', 5e-3), ('image_seg', 5e-3)):
+    for key, tol in (('image_raw', 1e-4), ('image_depth', 2e-5), ('image', 1e-4), ('image_seg', 1e-4)):
         a, b = out[key].float().cpu(), ref[key].float()
         scale = max(1.0, b.abs().max().item())
         report[key] = ((a - b).abs().max().item(), scale, tol)
@@ -55,4 +57,4 @@ def test_synthesis_on_gpu_matches_cpu_oracle(case, channels_last, chain, mm):
     for key, (err, scale, tol) in report.items():
         assert err <= tol * scale, (key, report)
     to8 = lambda t: (t * 127.5 + 128).clamp(0, 255).to(torch.uint8).int()
-    assert (to8(out['image'].float().cpu()) - to8(ref['image'])).abs().max() <= 2
+    assert (to8(out['image'].float().cpu()) - to8(ref['image'])).abs().max() <= 1
