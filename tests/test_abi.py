@@ -34,7 +34,7 @@ def test_struct_sizes_match_header():
     probe = r'''
     #include <stdio.h>
     #include "ide3d_b200.h"
-    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(ide3d_upfirdn2d_params), sizeof(ide3d_filtered_lrelu_params),
+    int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(ide3d_fir_epilogue), sizeof(ide3d_upfirdn2d_params), sizeof(ide3d_filtered_lrelu_params),
         sizeof(ide3d_filtered_lrelu_act_params), sizeof(ide3d_triplane), sizeof(ide3d_mlp_head), sizeof(ide3d_decoder),
         sizeof(ide3d_raymarch_params)); return 0; }'''
     with tempfile.TemporaryDirectory() as d:
@@ -43,7 +43,7 @@ def test_struct_sizes_match_header():
         exe = os.path.join(d, 'p')
         subprocess.run(['gcc', '-I', os.path.join(ROOT, 'include'), c, '-o', exe], check=True)
         sizes = [int(v) for v in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split()]
-    ours = [ctypes.sizeof(t) for t in (_lib.UpfirParams, _lib.FlreluParams, _lib.FlreluActParams, _lib.TriPlane,
+    ours = [ctypes.sizeof(t) for t in (_lib.FirEpilogue, _lib.UpfirParams, _lib.FlreluParams, _lib.FlreluActParams, _lib.TriPlane,
                                        _lib.MlpHead, _lib.Decoder, _lib.RaymarchParams)]
     assert ours == sizes
 
@@ -54,6 +54,13 @@ def test_invalid_arguments_return_status_not_crash(lib):
     assert b'null params' in lib.ide3d_last_error()
     assert lib.ide3d_upfirdn2d(None, None) == _lib.INVALID
     assert lib.ide3d_bias_act(None, None, None, None, None, None, 0, 0, 1, 0.0, 1.0, -1.0, 16, 0, 1, None) == _lib.INVALID
+    # the fused extensions validate before they touch the device as well
+    assert lib.ide3d_modconv_epilogue(None, None, None, None, None, None, None, 0, 1, 0.0, 1.0, -1.0, 1, 4, 16, 1, 0, None) == _lib.INVALID
+    assert lib.ide3d_modconv_epilogue(None, None, None, None, None, None, None, 0, 1, 0.0, 1.0, -1.0, 0, 4, 16, 1, 0, None) == _lib.OK   # empty: no-op
+    assert lib.ide3d_upfirdn2d_add(None, None, 0, 0, 0, None, None) == _lib.INVALID and b'null add' in lib.ide3d_last_error()
+    assert lib.ide3d_upfirdn2d_epilogue(None, None, None) == _lib.INVALID and b'null epilogue' in lib.ide3d_last_error()
+    assert lib.ide3d_mask2color(None, 1, 0, 4, 4, 0, 0, 0, 0, None, None, 0, None) == _lib.INVALID
+    assert lib.ide3d_mask2color(None, 0, 19, 4, 4, 0, 0, 0, 0, None, None, 0, None) == _lib.OK                                           # empty batch
 
 
 def test_product_has_no_cpu_path():
