@@ -170,3 +170,16 @@ def test_mrc_writer_round_trip_and_mrcfile_shim(tmp_path):
     mrc.write_mrc(path, torch.from_numpy(vol).double(), voxel_size=0.5)
     back2, hdr2 = mrc.read_mrc(path)
     assert np.array_equal(back2, vol) and hdr2['cella'] == (4.5, 3.5, 2.5)
+
+
+def test_render_interp_video_batched_driver(G):
+    """gen_videos' frame loop as one batched, sharded call: frame grids come back in frame order with the cells side by side."""
+    from ide3d_b200 import video
+    with cpu_reference_ops():
+        grids = video.render_interp_video(G, seeds=[0, 1, 2, 3], w_frames=2, grid_dims=(2, 1), batch=2, truncation_cutoff=4,
+                                          device=torch.device('cpu'), synthesis_kwargs=dict(perturb=None))
+        ws, c, (F, gh, gw) = video.interp_video_inputs(G, [0, 1, 2, 3], w_frames=2, grid_dims=(2, 1), truncation_cutoff=4, device=torch.device('cpu'))
+        one = G.synthesis(ws[2:3].float(), c=c[2:3], noise_mode='const', perturb=None)          # frame 1, cell 0
+    assert grids.dtype == torch.uint8 and tuple(grids.shape) == (4, 64, 128, 3) and (F, gh, gw) == (4, 1, 2)
+    want = (one[0] * 127.5 + 128).clamp(0, 255).to(torch.uint8).permute(1, 2, 0)
+    assert (grids[1, :, :64].int() - want.int()).abs().max() <= 1

@@ -121,3 +121,50 @@ def test_extract_shapes_main_writes_mrc_through_the_shim(ref_env, tmp_path, monk
     grid = np.load(out / '0.npy')
     vol, hdr = mrc.read_mrc(str(out / '0.mrc'))
     assert grid.shape == (10, 10, 10) and np.array_equal(vol, grid.astype(np.float32)) and hdr['mode'] == 2
+
+
+def test_batched_video_inputs_equal_the_reference_frame_loop(ref_env):
+    """ide3d_b200.video.interp_video_inputs computes, up front, exactly the (w, camera) pair the reference's frame loop hands to
+    G.synthesis for every (frame, grid cell) (gen_videos.py:112-129) -- recorded here from the unmodified gen_interp_video -- and
+    layout_frames is layout_grid (gen_videos.py:24-38) applied per frame."""
+    G, dev = ref_env
+    from ide3d_b200 import video
+    calls = []
+
+    class Recorder:
+        z_dim = G.z_dim
+        mapping = staticmethod(G.mapping)
+
+        def parameters(self):
+            return G.parameters()
+
+        @staticmethod
+        def synthesis(ws, c, **kw):
+            calls.append((ws.detach().clone(), c.detach().clone()))
+            n = ws.shape[0]
+            return torch.zeros(n, 3, 4, 4), torch.zeros(n, 19, 4, 4)
+
+    class _Writer:
+        def append_data(self, a):
+            pass
+
+        def close(self):
+            pass
+
+    sys.modules['imageio'].get_writer = lambda *a, **k: _Writer()
+    gv = importlib.import_module('gen_videos')
+    kw = dict(seeds=[3, 1, 4, 1, 5, 9, 2, 6], w_frames=3, grid_dims=(2, 1), psi=0.7, truncation_cutoff=4)
+    gv.gen_interp_video(Recorder(), 'unused.mp4', image_mode='image_seg', device=torch.device('cpu'), **kw)
+    calls = calls[1:]                                                           # the warm-up call (:89)
+    ws, c, (F, gh, gw) = video.interp_video_inputs(Recorder(), device=torch.device('cpu'), **kw)
+    assert (F, gh, gw) == (12, 1, 2) and len(calls) == F * gh * gw == ws.shape[0] == c.shape[0]
+    ref_ws = torch.cat([w for w, _ in calls])
+    ref_c = torch.cat([cc for _, cc in calls])
+    assert ws.dtype == ref_ws.dtype == torch.float64
+    assert (ws - ref_ws).abs().max() < 1e-9 and (c - ref_c).abs().max() < 1e-6
+
+    frames = torch.randint(0, 255, (F * gh * gw, 3, 5, 7), dtype=torch.uint8)
+    mine = video.layout_frames(frames, F, gh, gw)
+    for f in range(F):
+        want = gv.layout_grid(frames[f * gh * gw:(f + 1) * gh * gw], grid_w=gw, grid_h=gh, float_to_uint8=False)
+        assert np.array_equal(mine[f].numpy(), want)
