@@ -312,9 +312,101 @@ def g_conv2d_resample():
     save('conv2d_resample', x=x, w3=w3, w1=w1, wg=wg, f=f, **out)
 
 
+def g_networks():
+    """a13: the reference's own layer classes (inversion/networks.py: MappingNetwork :246, SynthesisBlock :718, SegSynthesisBlock
+    :966, with SynthesisLayer :330 / ToRGBLayer :670 / modulated_conv2d :55 inside) run on CPU with seeded parameters; the product's
+    restatement (ide3d_b200.training.networks) must LOAD THE SAME state_dict and reproduce the outputs.  inversion/networks.py needs two
+    dead numpy-1.x imports stubbed -- no source edit."""
+    import types
+    for name, attr in (('numpy.lib.arraysetops', 'isin'), ('numpy.lib.function_base', 'angle')):
+        m = types.ModuleType(name)
+        setattr(m, attr, getattr(np, attr))
+        sys.modules.setdefault(name, m)
+    import inversion.networks as rn
+    from ide3d_b200.training import networks as mine
+    from oracle.backend import cpu_reference_ops
+    layer = dict(layer_name='inversion.networks.SynthesisLayer')
+    out = {}
+
+    def randomise(mod, gen):
+        for p in mod.parameters():                       # StyleGAN init leaves biases / noise strengths at 0: make every term count
+            if p.ndim == 0:
+                p.data.fill_(0.3)
+            elif p.ndim == 1:
+                p.data.copy_(torch.randn(p.shape, generator=gen) * 0.5)
+
+    def put(prefix, sd):
+        for k, v in sd.items():
+            out[f'{prefix}/{k}'] = v.detach().clone()
+
+    g = torch.Generator().manual_seed(11)
+    torch.manual_seed(11)
+    # ---- mapping
+    rm = rn.MappingNetwork(z_dim=16, c_dim=25, w_dim=12, num_ws=5, num_layers=2).eval()
+    rm.w_avg.copy_(torch.randn(12, generator=g) * 0.1)
+    z, c = torch.randn(3, 16, generator=g), torch.randn(3, 25, generator=g)
+    with torch.no_grad():
+        w_ref = rm(z, c, truncation_psi=0.7, truncation_cutoff=3)
+    mm = mine.MappingNetwork(z_dim=16, c_dim=25, w_dim=12, num_ws=5, num_layers=2).eval()
+    mm.load_state_dict(rm.state_dict())
+    with torch.no_grad(), cpu_reference_ops():
+        close(mm(z, c, truncation_psi=0.7, truncation_cutoff=3), w_ref, 2e-6, 'mapping')
+    put('map', rm.state_dict())
+    out.update(map_z=z, map_c=c, map_ws=w_ref)
+
+    # ---- SynthesisBlock: first block (const input) and an upsampling block, eval (grouped weight-modulated conv) and train
+    #      (activation-scaled conv) forms of modulated_conv2d
+    for tag, in_ch in (('b0', 0), ('b1', 16)):
+        rb = rn.SynthesisBlock(in_ch, 8, w_dim=12, resolution=16, img_channels=6, is_last=False, architecture='skip', **layer)
+        randomise(rb, g)
+        mb = mine.SynthesisBlock(in_ch, 8, w_dim=12, resolution=16, img_channels=6, is_last=False)
+        mb.load_state_dict(rb.state_dict())
+        x = torch.randn(2, 16, 8, 8, generator=g) if in_ch else None
+        img = torch.randn(2, 6, 8, 8, generator=g) if in_ch else None
+        ws = torch.randn(2, 3 if in_ch else 2, 12, generator=g)
+        put(tag, rb.state_dict())
+        out[f'{tag}_ws'] = ws
+        if in_ch:
+            out[f'{tag}_x'], out[f'{tag}_img'] = x, img
+        for mode in ('eval', 'train'):
+            getattr(rb, mode)(); getattr(mb, mode)()
+            with torch.no_grad():
+                xo, io = rb(x, None if img is None else img.clone(), ws, noise_mode='const')
+                with cpu_reference_ops():
+                    xm, im = mb(x, None if img is None else img.clone(), ws, noise_mode='const')
+            close(xm, xo, 1e-5, f'{tag} {mode} x'); close(im, io, 1e-5, f'{tag} {mode} img')
+            out[f'{tag}_{mode}_x'], out[f'{tag}_{mode}_img'] = xo, io
+
+    # ---- SegSynthesisBlock (dual path).  The reference class has separate torgb / toseg layers; the product evaluates both heads
+    #      as one 1x1 modulated convolution with ONE affine (the real generator's block has three children, DESIGN.md §3), which is
+    #      the same function exactly when the two affines coincide -- so the golden case ties toseg.affine to torgb.affine.
+    rs = rn.SegSynthesisBlock(16, 8, w_dim=12, resolution=16, img_channels=6, seg_channels=4, is_last=False, architecture='skip', **layer)
+    randomise(rs, g)
+    rs.toseg.affine.load_state_dict(rs.torgb.affine.state_dict())
+    ms = mine.SegSynthesisBlock(16, 8, w_dim=12, resolution=16, img_channels=6, seg_channels=4, is_last=False)
+    sd = {k: v for k, v in rs.state_dict().items() if not k.startswith(('torgb.', 'toseg.'))}
+    sd['torgb.weight'] = torch.cat([rs.torgb.weight, rs.toseg.weight], 0)
+    sd['torgb.bias'] = torch.cat([rs.torgb.bias, rs.toseg.bias], 0)
+    sd['torgb.affine.weight'], sd['torgb.affine.bias'] = rs.torgb.affine.weight, rs.torgb.affine.bias
+    ms.load_state_dict(sd)
+    x, img, seg = torch.randn(2, 16, 8, 8, generator=g), torch.randn(2, 6, 8, 8, generator=g), torch.randn(2, 4, 8, 8, generator=g)
+    ws = torch.randn(2, 3, 12, generator=g)
+    rs.eval(); ms.eval()
+    with torch.no_grad():
+        xo, io, so = rs(x, img.clone(), seg.clone(), ws, noise_mode='const')
+        with cpu_reference_ops():
+            xm, im, sm = ms(x, img.clone(), ws, condition_img=seg.clone(), noise_mode='const')
+    close(xm, xo, 1e-5, 'seg x'); close(im, io, 1e-5, 'seg img'); close(sm, so, 1e-5, 'seg seg')
+    put('seg', sd)
+    out.update(seg_x=x, seg_img=img, seg_seg=seg, seg_ws=ws, seg_out_x=xo, seg_out_img=io, seg_out_seg=so)
+    save('networks', **out)
+
+
 if __name__ == '__main__':
     torch.set_num_threads(4)
-    for fn in (g_rays, g_transform, g_camera, g_triplane, g_integration, g_pdf, g_chain, g_create_samples,
-               g_bias_act, g_upfirdn2d, g_filtered_lrelu, g_conv2d_resample):
-        fn()
+    fns = dict(rays=g_rays, transform=g_transform, camera=g_camera, triplane=g_triplane, integration=g_integration, pdf=g_pdf,
+               chain=g_chain, create_samples=g_create_samples, bias_act=g_bias_act, upfirdn2d=g_upfirdn2d,
+               filtered_lrelu=g_filtered_lrelu, conv2d_resample=g_conv2d_resample, networks=g_networks)
+    for name in (sys.argv[1:] or list(fns)):              # `make_golden.py networks` regenerates one fixture only
+        fns[name]()
     print('all reference outputs reproduced by oracle/ within tolerance')

@@ -58,3 +58,40 @@ def test_synthesis_on_gpu_matches_cpu_oracle(case, channels_last, chain, mm):
         assert err <= tol * scale, (key, report)
     to8 = lambda t: (t * 127.5 + 128).clamp(0, 255).to(torch.uint8).int()
     assert (to8(out['image'].float().cpu()) - to8(ref['image'])).abs().max() <= 1
+
+
+@pytest.mark.parametrize('channels_last', [True, False])
+def test_blocks_on_gpu_reproduce_recorded_reference_classes(channels_last):
+    """tests/golden/networks.npz (outputs of the reference's own MappingNetwork / SynthesisBlock / SegSynthesisBlock, see
+    tests/test_oracle_golden.py) replayed through the CUDA path: same state_dicts, sm_100a ops, fp32 convolutions."""
+    import numpy as np
+    from conftest import load_golden
+    from ide3d_b200.training import networks as nw
+    g = load_golden('networks')
+    T_ = lambda k: torch.from_numpy(np.asarray(g[k])).cuda()
+    sd = lambda prefix: {k[len(prefix) + 1:]: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith(prefix + '/')}
+    saved = (nw.CHANNELS_LAST, torch.backends.cudnn.allow_tf32)
+    try:
+        nw.CHANNELS_LAST, torch.backends.cudnn.allow_tf32 = channels_last, False
+        with torch.no_grad():
+            mm = nw.MappingNetwork(z_dim=16, c_dim=25, w_dim=12, num_ws=5, num_layers=2).eval()
+            mm.load_state_dict(sd('map'))
+            mm.cuda()
+            assert (mm(T_('map_z'), T_('map_c'), truncation_psi=0.7, truncation_cutoff=3) - T_('map_ws')).abs().max() < 1e-5
+            for tag, in_ch in (('b0', 0), ('b1', 16)):
+                mb = nw.SynthesisBlock(in_ch, 8, w_dim=12, resolution=16, img_channels=6, is_last=False).eval()
+                mb.load_state_dict(sd(tag))
+                mb.cuda()
+                xo, io = mb(T_(f'{tag}_x') if in_ch else None, T_(f'{tag}_img').clone() if in_ch else None, T_(f'{tag}_ws'), noise_mode='const')
+                for got, key in ((xo, f'{tag}_eval_x'), (io, f'{tag}_eval_img')):
+                    ref = T_(key)
+                    assert (got.float() - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item()), (key, channels_last)
+            ms = nw.SegSynthesisBlock(16, 8, w_dim=12, resolution=16, img_channels=6, seg_channels=4, is_last=False).eval()
+            ms.load_state_dict(sd('seg'))
+            ms.cuda()
+            outs = ms(T_('seg_x'), T_('seg_img').clone(), T_('seg_ws'), condition_img=T_('seg_seg').clone(), noise_mode='const')
+            for got, key in zip(outs, ('seg_out_x', 'seg_out_img', 'seg_out_seg')):
+                ref = T_(key)
+                assert (got.float() - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item()), (key, channels_last)
+    finally:
+        nw.CHANNELS_LAST, torch.backends.cudnn.allow_tf32 = saved

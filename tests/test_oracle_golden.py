@@ -174,3 +174,39 @@ def test_conv2d_resample():
         kw = dict(kw)
         kw['w'] = T(g[kw['w']])
         assert_close(oops.conv2d_resample(x, **kw), g[k], 3e-5, what=k)
+
+
+def _load_prefixed(g, prefix):
+    return {k[len(prefix) + 1:]: torch.from_numpy(np.asarray(g[k])) for k in g if k.startswith(prefix + '/')}
+
+
+def test_networks_restatement_loads_reference_state_dicts_and_reproduces_outputs():
+    """a13: tests/golden/networks.npz holds state_dicts and outputs of the reference's OWN classes (inversion/networks.py
+    MappingNetwork, SynthesisBlock, SegSynthesisBlock; generated by make_golden.py::g_networks).  The product's modules load those
+    state_dicts unchanged (same parameter names and shapes) and, evaluated with the oracle ops, reproduce the recorded outputs --
+    in both forms of modulated_conv2d (eval: the reference's grouped weight-modulated conv vs the product's activation scaling;
+    train: activation scaling on both sides) and in both layouts."""
+    from ide3d_b200.training import networks as nw
+    from oracle.backend import cpu_reference_ops
+    g = load_golden('networks')
+    T_ = lambda k: torch.from_numpy(np.asarray(g[k]))
+    mm = nw.MappingNetwork(z_dim=16, c_dim=25, w_dim=12, num_ws=5, num_layers=2).eval()
+    mm.load_state_dict(_load_prefixed(g, 'map'))
+    with torch.no_grad(), cpu_reference_ops():
+        assert (mm(T_('map_z'), T_('map_c'), truncation_psi=0.7, truncation_cutoff=3) - T_('map_ws')).abs().max() < 2e-6
+    for layout in (True, False):
+        with torch.no_grad(), cpu_reference_ops(reference_layout=not layout):
+            for tag, in_ch in (('b0', 0), ('b1', 16)):
+                mb = nw.SynthesisBlock(in_ch, 8, w_dim=12, resolution=16, img_channels=6, is_last=False)
+                mb.load_state_dict(_load_prefixed(g, tag))
+                x = T_(f'{tag}_x') if in_ch else None
+                for mode in ('eval', 'train'):
+                    getattr(mb, mode)()
+                    img = T_(f'{tag}_img').clone() if in_ch else None
+                    xo, io = mb(x, img, T_(f'{tag}_ws'), noise_mode='const')
+                    assert (xo - T_(f'{tag}_{mode}_x')).abs().max() < 1e-5 and (io - T_(f'{tag}_{mode}_img')).abs().max() < 1e-5, (tag, mode, layout)
+            ms = nw.SegSynthesisBlock(16, 8, w_dim=12, resolution=16, img_channels=6, seg_channels=4, is_last=False).eval()
+            ms.load_state_dict(_load_prefixed(g, 'seg'))
+            xo, io, so = ms(T_('seg_x'), T_('seg_img').clone(), T_('seg_ws'), condition_img=T_('seg_seg').clone(), noise_mode='const')
+            for got, key in ((xo, 'seg_out_x'), (io, 'seg_out_img'), (so, 'seg_out_seg')):
+                assert (got - T_(key)).abs().max() < 1e-5, (key, layout)
