@@ -57,13 +57,6 @@ __device__ __forceinline__ float jitter_hash(uint32_t idx, uint32_t lo, uint32_t
 __device__ __forceinline__ float softplus_fast(float x) {
     return fmaxf(x, 0.f) + __logf(1.f + __expf(-fabsf(x)));
 }
-// same function on bare MUFU instructions (ftz forms: no denormal pre/post-scaling code around ex2 / lg2): 7 instructions
-__device__ __forceinline__ float softplus_mufu(float x) {
-    float t, l;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fabsf(x) * -1.4426950408889634f));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + t));
-    return fmaf(l, 0.6931471805599453f, fmaxf(x, 0.f));
-}
 // density activation: full precision, matters because delta_last = 1e10 amplifies tiny values
 __device__ __forceinline__ float softplus_precise(float x) {
     return fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
@@ -156,90 +149,11 @@ __device__ __forceinline__ void gather_chunk_to(const PlaneView& tex, const Plan
     }
 }
 
-// Channels-last fast path with explicit memory-level parallelism: for the 4 samples of a sub-iteration every lane first
-// builds its 12 tap addresses (clamped into the plane, out-of-range taps get weight 0 -- no branches), then issues the 12
-// texture loads back to back, accumulates, and repeats for the 12 shape loads.  Requires tex and seg to share strides.
-template <bool kAllInFlight = false, typename Store>
-__device__ __forceinline__ void gather_chunk_cl(const PlaneView& tex, const PlaneView& seg, int n, float cx, float cy,
-                                                float cz, int lane, Store store) {
-    const int W = tex.w, H = tex.h;
-    const Foot f0 = footprint(cx, cy, W, H);
-    const Foot f1 = footprint(cy, cz, W, H);
-    const Foot f2 = footprint(cx, cz, W, H);
-    const int q = lane & 7, grp = lane >> 3;
-    const float4* tb = reinterpret_cast<const float4*>(tex.base + (long long)n * tex.sn) + q;
-    const float4* sb = reinterpret_cast<const float4*>(seg.base + (long long)n * seg.sn) + q;
-    const int sh4 = (int)(tex.sh >> 2), sw4 = (int)(tex.sw >> 2);      // strides in float4 units (multiples of 4 floats)
-
-#pragma unroll 1
-    for (int it = 0; it < 8; ++it) {
-        const int src = it * 4 + grp;
-        int off[12];
-        float wgt[12];
-        bool any = false;
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const Foot& mine = (k == 0) ? f0 : (k == 1 ? f1 : f2);
-            const int x0 = __shfl_sync(kFull, mine.x0, src);
-            const int y0 = __shfl_sync(kFull, mine.y0, src);
-            const float fx = __shfl_sync(kFull, mine.fx, src);
-            const float fy = __shfl_sync(kFull, mine.fy, src);
-#pragma unroll
-            for (int tap = 0; tap < 4; ++tap) {
-                const int xx = x0 + (tap & 1), yy = y0 + (tap >> 1);
-                const bool ok = ((unsigned)xx < (unsigned)W) && ((unsigned)yy < (unsigned)H);
-                const int xc = min(max(xx, 0), W - 1), yc = min(max(yy, 0), H - 1);
-                off[k * 4 + tap] = yc * sh4 + xc * sw4 + k * (kFeat / 4);
-                const float wv = ((tap & 1) ? fx : 1.f - fx) * ((tap >> 1) ? fy : 1.f - fy);
-                wgt[k * 4 + tap] = ok ? wv : 0.f;
-                any |= ok;
-            }
-        }
-        float at[4] = {0.f, 0.f, 0.f, 0.f}, as[4] = {0.f, 0.f, 0.f, 0.f};
-        if (__any_sync(kFull, any)) {                           // fully masked sub-iterations (dead samples) load nothing
-            float4 v[12];
-            float4 u[kAllInFlight ? 12 : 1];
-#pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = __ldg(tb + off[i]);
-            if (kAllInFlight) {
-#pragma unroll
-                for (int i = 0; i < 12; ++i) u[kAllInFlight ? i : 0] = __ldg(sb + off[i]);     // all 24 LDG.128 in flight
-            }
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float p[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int tap = 0; tap < 4; ++tap) {
-                    const float4 a = v[k * 4 + tap];
-                    const float w_ = wgt[k * 4 + tap];
-                    p[0] += a.x * w_; p[1] += a.y * w_; p[2] += a.z * w_; p[3] += a.w * w_;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) at[j] += p[j];
-            }
-#pragma unroll
-            for (int i = 0; i < 12; ++i) v[i] = kAllInFlight ? u[kAllInFlight ? i : 0] : __ldg(sb + off[i]);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                float p[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int tap = 0; tap < 4; ++tap) {
-                    const float4 a = v[k * 4 + tap];
-                    const float w_ = wgt[k * 4 + tap];
-                    p[0] += a.x * w_; p[1] += a.y * w_; p[2] += a.z * w_; p[3] += a.w * w_;
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) as[j] += p[j];
-            }
-        }
-        store(src, q, at, as);
-    }
-}
-
 // Per-axis form of the same gather (tcgen05 producers): the three planes share their axes -- x is the column of planes 0 and
 // 2, y the row of plane 0 and the column of plane 1, z the row of planes 1 and 2 -- so the floor / fraction / validity /
 // clamp work is done once per axis role (4 roles) instead of once per tap (12 taps), and a tap's offset and weight are one
-// add and one multiply.  Same arithmetic as gather_chunk_cl: w = (x-weight or 0) * (y-weight or 0), identical products.
+// add and one multiply.  Same arithmetic as the per-tap form above: w = (x-weight or 0) * (y-weight or 0), identical products.
+// Taps whose weight is 0 (outside the plane) read a clamped, valid address -- no branches; all 24 LDG.128 of a pass are in flight.
 struct AxisFoot {
     int i0;
     float f;
@@ -282,7 +196,7 @@ __device__ __forceinline__ void gather_chunk_axes(const PlaneView& tex, const Pl
         const AxisTaps Yr = axis_taps(__shfl_sync(kFull, ayr.i0, src), __shfl_sync(kFull, ayr.f, src), H, sh4);  // row of plane 0
         const AxisTaps Yc = axis_taps(__shfl_sync(kFull, ayc.i0, src), __shfl_sync(kFull, ayc.f, src), W, sw4);  // column of plane 1
         const AxisTaps Z = axis_taps(__shfl_sync(kFull, az.i0, src), __shfl_sync(kFull, az.f, src), H, sh4);     // row of planes 1, 2
-        // tap order inside a plane as in gather_chunk_cl: (col lo,row lo) (col hi,row lo) (col lo,row hi) (col hi,row hi)
+        // tap order inside a plane: (col lo,row lo) (col hi,row lo) (col lo,row hi) (col hi,row hi)
         float4 v[12], u[12];
 #define IDE3D_PLANE_LOADS(k, C, R)                                                                                 \
         {                                                                                                         \
