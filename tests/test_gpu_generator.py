@@ -95,3 +95,21 @@ def test_blocks_on_gpu_reproduce_recorded_reference_classes(channels_last):
                 assert (got.float() - ref).abs().max() <= 1e-4 * max(1.0, ref.abs().max().item()), (key, channels_last)
     finally:
         nw.CHANNELS_LAST, torch.backends.cudnn.allow_tf32 = saved
+
+
+def test_stream_frames_matches_batch_loop_and_lands_in_pinned_host_memory(case):
+    """dist.stream_frames_sharded (H2D from pinned inputs, render, uint8, D2H on a side stream overlapping the next batch) returns the
+    same frames as the plain batch loop render_frames_sharded; result lives in page-locked host memory."""
+    from ide3d_b200 import dist as idist
+    G, ws, c, kw, ref = case
+    Gd = G.cuda()
+    try:
+        ws4, c4 = ws.repeat(2, 1, 1).pin_memory(), c.repeat(2, 1).pin_memory()
+        skw = dict(noise_mode='const', num_steps=24, perturb=None)
+        streamed = idist.stream_frames_sharded(Gd, ws4, c4, 0, 1, batch=2, **skw)
+        looped = idist.render_frames_sharded(Gd, ws4.cuda(), c4.cuda(), 0, 1, batch=4, **skw)
+    finally:
+        G.cpu()
+    assert streamed.dtype == torch.uint8 and streamed.device.type == 'cpu' and streamed.is_pinned() and tuple(streamed.shape) == (4, 3, 128, 128)
+    assert (streamed.int() - looped.cpu().int()).abs().max() <= 1            # batch 2 vs batch 4: cuDNN may pick different algorithms
+    assert torch.equal(streamed[:2], streamed[2:])                           # the two halves are the same inputs
