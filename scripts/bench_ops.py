@@ -67,6 +67,35 @@ def main():
                                   'ms': round(ms, 4), 'algorithmic_GB': round(nbytes / 1e9, 3), 'achieved_GBs': round(gbs, 1), 'peak_GBs': pk, 'frac': round(gbs / pk, 3)}), flush=True)
                 del y
 
+    # ---- the fused forms on the shapes of the synthesis step (NHWC fp32, batch 8): algorithmic bytes = every tensor once
+    def fused_case(name, fn, nbytes):
+        try:
+            ms, y = timeit(fn)
+        except Exception as e:          # noqa
+            print(json.dumps({'op': name, 'error': str(e)[:200]}))
+            return
+        gbs = nbytes / ms / 1e6
+        print(json.dumps({'op': name, 'dtype': 'float32', 'layout': 'channels_last', 'ms': round(ms, 4), 'algorithmic_GB': round(nbytes / 1e9, 3),
+                          'achieved_GBs': round(gbs, 1), 'peak_GBs': pk, 'frac': round(gbs / pk, 3)}), flush=True)
+
+    cl = lambda t: t.contiguous(memory_format=torch.channels_last)
+    n = 2 if args.small else 8
+    xt = cl(torch.randn(n, 64, 513, 513, device='cuda'))                       # b512.conv0: transposed-conv output
+    d, s2, bb = torch.rand(n, 64, device='cuda') + 0.5, torch.rand(n, 64, device='cuda') + 0.5, torch.randn(64, device='cuda')
+    nz = torch.randn(512, 512, device='cuda')
+    fused_case('upfirdn2d_epilogue b512.conv0 (FIR + demod + noise + bias + lrelu -> x*s1)',
+               lambda: upfirdn2d.upfirdn2d_epilogue(xt, f4, padding=[1, 1, 1, 1], gain=4, scale=d, noise=nz, b=bb, act='lrelu', next_scale=s2, only_next=True),
+               (xt.numel() + n * 64 * 512 * 512) * 4)
+    xc = cl(torch.randn(n, 64, 512, 512, device='cuda'))                       # b512.conv1 output
+    fused_case('scaled_bias_act b512.conv1 (demod + noise + bias + lrelu -> x and x*s_rgb)',
+               lambda: bias_act.scaled_bias_act(xc, scale=d, noise=nz, b=bb, act='lrelu', next_scale=s2), 3 * xc.numel() * 4)
+    fused_case('scaled_bias_act modulation only (x * styles)', lambda: bias_act.scaled_bias_act(xc, scale=d), 2 * xc.numel() * 4)
+    img = cl(torch.randn(n, 96, 128, 128, device='cuda'))                      # vb256 skip step
+    ywide = cl(torch.randn(n, 192, 256, 256, device='cuda'))
+    b96 = torch.randn(96, device='cuda')
+    fused_case('upsample2d_add vb256 (upsample2d(img) + y[:, :96] + b)', lambda: upfirdn2d.upsample2d_add(img, f4, ywide[:, :96], b96),
+               (img.numel() + 2 * n * 96 * 256 * 256) * 4)
+
 
 if __name__ == '__main__':
     main()
