@@ -55,7 +55,7 @@ def ref_env(monkeypatch):
 
     with cpu_reference_ops():
         yield G, _Dev()
-    ours = {'training', 'torch_utils', 'dnnlib', 'legacy', 'gen_images', 'gen_videos', 'extract_shapes', 'camera_utils', 'mrcfile'}
+    ours = {'training', 'torch_utils', 'dnnlib', 'legacy', 'gen_images', 'gen_videos', 'extract_shapes', 'camera_utils', 'mrcfile', 'viz'}
     for k in list(sys.modules):                          # drop only what this fixture introduced (cv2 & co. cannot re-import)
         if k not in saved and k.split('.')[0] in ours:
             del sys.modules[k]
@@ -168,3 +168,50 @@ def test_batched_video_inputs_equal_the_reference_frame_loop(ref_env):
     for f in range(F):
         want = gv.layout_grid(frames[f * gh * gw:(f + 1) * gh * gw], grid_w=gw, grid_h=gh, float_to_uint8=False)
         assert np.array_equal(mine[f].numpy(), want)
+
+
+def test_viz_renderer_render_impl_runs_unchanged(ref_env, monkeypatch):
+    """viz/renderer.py (the interactive visualizer's backend, imported unmodified): Renderer._render_impl walks the generator contract
+    -- get_network (deepcopy + .to), G.img_resolution / G.synthesis.num_ws / named_buffers / G.mapping.w_avg / G.backbone.num_ws,
+    positional G.synthesis(w, c, noise_mode=, force_fp32=), forward hooks on every sub-module -- on CPU, with CUDA-only plumbing
+    (events, pinned buffers, the literal 'cuda' device) neutralised and matplotlib (absent) stubbed."""
+    G, dev = ref_env
+
+    class _Event:
+        def __init__(self, *a, **k):
+            pass
+
+        def record(self, *a):
+            pass
+
+        def synchronize(self):
+            pass
+
+        def elapsed_time(self, other):
+            return 0.0
+
+    for name in ('matplotlib', 'matplotlib.cm'):
+        monkeypatch.setitem(sys.modules, name, types.ModuleType(name))
+    sys.modules['matplotlib'].cm = sys.modules['matplotlib.cm']
+    monkeypatch.setattr(torch.cuda, 'Event', _Event)
+    monkeypatch.setattr(torch.Tensor, 'pin_memory', lambda self, *a, **k: self)
+    real_to = torch.nn.Module.to
+
+    def to_cpu_when_cuda(self, *args, **kwargs):
+        args = tuple('cpu' if (isinstance(a, str) and a.startswith('cuda')) or (isinstance(a, torch.device) and a.type == 'cuda') else a for a in args)
+        return real_to(self, *args, **kwargs)
+
+    monkeypatch.setattr(torch.nn.Module, 'to', to_cpu_when_cuda)
+    vr = importlib.import_module('viz.renderer')
+    import dnnlib
+    R = vr.Renderer()
+    R._device = torch.device('cpu')
+    res = dnnlib.EasyDict()
+    R._render_impl(res, pkl='unused.pkl', w0_seeds=[[0, 0.75], [1, 0.25]], stylemix_idx=[1, 2], stylemix_seed=2, trunc_psi=0.7, trunc_cutoff=4,
+                   yaw=0.2, pitch=0.1)
+    assert 'error' not in res
+    assert res.img_resolution == 64 and res.num_ws == G.synthesis.num_ws and res.has_noise and not res.has_input_transform
+    assert res.image.dtype == torch.uint8 and tuple(res.image.shape) == (64, 64, 3)
+    names = [l.name for l in res.layers]
+    assert 'synthesis' in names and any(n.startswith('synthesis.vb32') for n in names) and any(n.startswith('synthesis.b64') for n in names)
+    assert res.stats.shape == (6,) and torch.isfinite(res.stats).all()
