@@ -286,7 +286,7 @@ def main():
         for a, b in ev3:
             flush.zero_()
             a.record()
-            G.synthesis.renderer(img_v, seg_v, cam, img_size=RENDER, num_steps=NUM_STEPS)   # NCHW planes in: 2 layout passes + ray-march
+            G.synthesis.renderer(img_v, seg_v, cam, img_size=RENDER, num_steps=NUM_STEPS)   # planes as the backbone delivers them (NHWC: no layout pass; NCHW with IDE3D_CHANNELS_LAST=0: + 2 passes)
             b.record()
         torch.cuda.synchronize()
         renderer_ms = float(np.mean([a.elapsed_time(b) for a, b in ev3]))
