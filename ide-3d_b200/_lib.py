@@ -87,6 +87,37 @@ class RaymarchParams(C.Structure):
 _lib = None
 
 
+class _StreamHandle(int):
+    """cudaStream_t as an int that remembers which device it belongs to (see _GuardedLib)."""
+    device = None
+
+
+class _GuardedLib:
+    """Every ide3d_* entry point takes the stream as its LAST argument, and every caller builds it with
+    stream_ptr(tensor.device).  The wrapper makes that device current around the call -- the OptionalCUDAGuard(device_of(x))
+    of the reference plugins (upfirdn2d.cpp:34, bias_act.cpp:54) -- so the launch and the SM-count / occupancy queries inside
+    the library refer to the tensors' own device even when another one is current."""
+
+    def __init__(self, lib):
+        self._lib = lib
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if not name.startswith('ide3d_'):
+            return fn
+
+        def call(*args):
+            dev = getattr(args[-1], 'device', None) if args else None
+            if dev is None:
+                return fn(*args)
+            with torch.cuda.device(dev):
+                return fn(*args)
+
+        call.__name__ = name
+        self.__dict__[name] = call
+        return call
+
+
 def get_lib():
     """Load the shared library once.  Raises if it has not been built (python ide-3d_b200/build.py)."""
     global _lib
@@ -123,8 +154,8 @@ def get_lib():
         getattr(lib, 'ide3d_' + name).restype = C.c_int
     if lib.ide3d_abi_version() != 1:
         raise RuntimeError('ide3d_b200: ABI version mismatch between _lib.py and libide3d_b200.so')
-    _lib = lib
-    return lib
+    _lib = _GuardedLib(lib)
+    return _lib
 
 
 def exported_symbols():
@@ -151,6 +182,15 @@ def require_cuda(*tensors):
                                '(the CPU restatement lives in oracle/ and is test infrastructure only)')
 
 
+def forbid_grad(name, *tensors):
+    """The stage free functions write into fresh buffers through ctypes: their outputs carry no grad_fn.  Fail up front
+    instead of silently cutting the graph when a caller tries to back-propagate through them (the reference module is a
+    differentiable implementation); the differentiable route is render.raymarch / render_grad.RaymarchFunction."""
+    if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise RuntimeError(f'ide3d_b200.{name}: inputs require grad, but this stage kernel is forward-only -- use '
+                           f'ide3d_b200.render.raymarch (fused forward, render_grad backward) or wrap the call in torch.no_grad()')
+
+
 def dtype_code(t):
     try:
         return _DTYPES[t.dtype]
@@ -163,7 +203,10 @@ def ptr(t):
 
 
 def stream_ptr(device=None):
-    return torch.cuda.current_stream(device).cuda_stream
+    """Current stream of `device` as a cudaStream_t handle that carries the device (the guard in _GuardedLib reads it)."""
+    h = _StreamHandle(torch.cuda.current_stream(device).cuda_stream)
+    h.device = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    return h
 
 
 def launch_count():

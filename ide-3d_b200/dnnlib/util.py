@@ -31,6 +31,7 @@ class EasyDict(dict):
 
 def sample_from_triplane(coordinates, grid):
     L.require_cuda(coordinates, grid)
+    L.forbid_grad('sample_from_triplane', coordinates, grid)
     n, p, _ = coordinates.shape
     if grid.shape[0] != n:
         grid = grid.expand(n, -1, -1, -1)

@@ -73,10 +73,37 @@ class _BiasAct(torch.autograd.Function):
             dy = dy.contiguous(memory_format=torch.channels_last) if ctx.cl else dy.contiguous()
             dx = dy
             if spec.cuda_idx != 1 or gain != 1 or clamp >= 0:
-                dx = _plugin.bias_act(dy, b, x, y, None, 1, dim, spec.cuda_idx, alpha, gain, clamp)
+                dx = _BiasActGrad.apply(dy, x, b, y, dim, spec, alpha, gain, clamp)
         if ctx.needs_input_grad[1] and ctx.has_bias:
             db = dx.sum([i for i in range(dx.ndim) if i != dim])
         return dx, db, None, None, None, None, None
+
+
+class _BiasActGrad(torch.autograd.Function):
+    """dx = dy * gain * act'(x + b) (grad=1 kernel); its own backward uses the grad=2 kernel for the second-order term, so
+    double backward (R1 / path-length regularisers) is exact -- the reference's BiasActCudaGrad, bias_act.py:178-203."""
+
+    @staticmethod
+    def forward(ctx, dy, x, b, y, dim, spec, alpha, gain, clamp):
+        ctx.cfg = (dim, spec, alpha, gain, clamp)
+        ctx.cl = (dy.ndim == 4 and not dy.is_contiguous())
+        dx = _plugin.bias_act(dy, b, x, y, None, 1, dim, spec.cuda_idx, alpha, gain, clamp)
+        ctx.save_for_backward(dy if spec.has_2nd_grad else None, x, b, y)
+        return dx
+
+    @staticmethod
+    def backward(ctx, d_dx):
+        dim, spec, alpha, gain, clamp = ctx.cfg
+        d_dx = d_dx.contiguous(memory_format=torch.channels_last) if ctx.cl else d_dx.contiguous()
+        dy, x, b, y = ctx.saved_tensors
+        d_dy = d_x = d_b = None
+        if ctx.needs_input_grad[0]:
+            d_dy = _BiasActGrad.apply(d_dx, x, b, y, dim, spec, alpha, gain, clamp)
+        if spec.has_2nd_grad and (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]):
+            d_x = _plugin.bias_act(d_dx, b, x, y, dy, 2, dim, spec.cuda_idx, alpha, gain, clamp)
+        if spec.has_2nd_grad and ctx.needs_input_grad[2]:
+            d_b = d_x.sum([i for i in range(d_x.ndim) if i != dim])
+        return d_dy, d_x, d_b, None, None, None, None, None, None
 
 
 def bias_act(x, b=None, dim=1, act='linear', alpha=None, gain=None, clamp=None, impl='cuda'):

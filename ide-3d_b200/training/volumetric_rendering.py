@@ -55,6 +55,7 @@ def fancy_integration(rgb_sigma, rays_d_cam, z_vals, device, noise_std=0.5, last
     if fill_mode == 'debug':
         raise NotImplementedError("fill_mode='debug' paints 3-channel pixels and cannot apply to feature maps")
     _cuda_only(rgb_sigma, rays_d_cam, z_vals)
+    L.forbid_grad('fancy_integration', rgb_sigma, rays_d_cam, z_vals)
     n, R, S, Cc = rgb_sigma.shape
     rs, d, z = _f32(rgb_sigma), _f32(rays_d_cam), _f32(z_vals)
     noise = torch.randn([n, R, S], device=rs.device, dtype=torch.float32) if noise_std else None
@@ -92,6 +93,7 @@ _IDENTITY = {}
 
 def _transform(points, z_vals, ray_directions, u, cam):
     _cuda_only(points, z_vals, ray_directions, cam)
+    L.forbid_grad('transform_sampled_points / perturb_points', points, z_vals, ray_directions, cam)
     n, R, S, _ = points.shape
     p, z, d, c = _f32(points), _f32(z_vals), _f32(ray_directions), _f32(cam).reshape(n, 16)
     dev = p.device
@@ -203,6 +205,7 @@ def create_world2cam_matrix(forward_vector, origin, device=None):
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
     """Inverse-CDF importance sampling: bins [R, S+1], weights [R, S] -> samples [R, N_importance]."""
     _cuda_only(bins, weights)
+    L.forbid_grad('sample_pdf', bins, weights)
     n_rays, n_s = weights.shape
     if det:
         u = torch.linspace(0, 1, N_importance, device=bins.device).expand(n_rays, N_importance)

@@ -19,6 +19,25 @@ def peak():
     return float(json.load(open(p))['hbm_gbs']) if os.path.exists(p) else 6650.0
 
 
+def load_reference_ops():
+    """The reference's own torch_utils.ops wrappers on the reference's own CUDA plugins, prebuilt for sm_100a by
+    baseline/build_ref_plugins.py (custom_ops._cached_plugins is pre-seeded, so get_plugin returns them without a JIT build)."""
+    import importlib.util
+    ref = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref, 'plugins')):
+        return None
+    sys.path.insert(0, ref)
+    from torch_utils import custom_ops as rco
+    rco.verbosity = 'none'
+    for name in ('bias_act_plugin', 'upfirdn2d_plugin', 'filtered_lrelu_plugin'):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(ref, 'plugins', name, name + '.so'))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        rco._cached_plugins[name] = mod
+    from torch_utils.ops import bias_act as r_ba, filtered_lrelu as r_fl, upfirdn2d as r_up
+    return r_ba, r_fl, r_up
+
+
 def timeit(fn, reps=10, warm=3):
     flush = torch.empty(256 * 1024 * 1024 // 4, device='cuda')
     for _ in range(warm):
@@ -36,35 +55,49 @@ def timeit(fn, reps=10, warm=3):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--small', action='store_true')
+    ap.add_argument('--no-ref', action='store_true', help='skip the reference plugins (baseline/_ref)')
     args = ap.parse_args()
     C = 64 if args.small else 512
     pk = peak()
     f4 = upfirdn2d.setup_filter([1, 3, 3, 1], device='cuda')
     import scipy.signal
     f12 = torch.as_tensor(scipy.signal.firwin(numtaps=12, cutoff=0.25, width=0.5), dtype=torch.float32, device='cuda')
+    refops = None if args.no_ref else load_reference_ops()
     for dtype in (torch.float32, torch.float16):
         x = torch.randn(1, C, 512, 512, device='cuda', dtype=dtype)
         b = torch.randn(C, device='cuda', dtype=dtype)
+        flkw = dict(fu=f12, fd=f12, b=b, up=2, down=2, padding=[10, 11, 10, 11], gain=2 ** 0.5, slope=0.2, clamp=256)
         cases = {
-            'bias_act lrelu+clamp': lambda: bias_act.bias_act(x, b, act='lrelu', clamp=256),
-            'upfirdn2d upsample2d 4x4': lambda: upfirdn2d.upsample2d(x, f4),
-            'upfirdn2d filter2d 4x4': lambda: upfirdn2d.filter2d(x, f4),
-            'upfirdn2d downsample2d 4x4': lambda: upfirdn2d.downsample2d(x, f4),
-            'filtered_lrelu up2 down2 12-tap': lambda: filtered_lrelu.filtered_lrelu(x, fu=f12, fd=f12, b=b, up=2, down=2, padding=[10, 11, 10, 11], gain=2 ** 0.5, slope=0.2, clamp=256),
+            'bias_act lrelu+clamp': lambda m: m[0].bias_act(x, b, act='lrelu', clamp=256),
+            'upfirdn2d upsample2d 4x4': lambda m: m[2].upsample2d(x, f4),
+            'upfirdn2d filter2d 4x4': lambda m: m[2].filter2d(x, f4),
+            'upfirdn2d downsample2d 4x4': lambda m: m[2].downsample2d(x, f4),
+            'filtered_lrelu up2 down2 12-tap': lambda m: m[1].filtered_lrelu(x, **flkw),
         }
+        ours = (bias_act, filtered_lrelu, upfirdn2d)
         for layout in ('contiguous', 'channels_last'):
             if layout == 'channels_last':
                 x = x.contiguous(memory_format=torch.channels_last)
             for name, fn in cases.items():
                 try:
-                    ms, y = timeit(fn)
+                    ms, y = timeit(lambda: fn(ours))
                 except Exception as e:          # noqa
                     print(json.dumps({'op': name, 'dtype': str(dtype), 'layout': layout, 'error': str(e)[:200]}))
                     continue
                 nbytes = (x.numel() + y.numel()) * x.element_size()
                 gbs = nbytes / ms / 1e6
-                print(json.dumps({'op': name, 'dtype': str(dtype).replace('torch.', ''), 'layout': layout, 'shape': list(x.shape), 'out': list(y.shape),
-                                  'ms': round(ms, 4), 'algorithmic_GB': round(nbytes / 1e9, 3), 'achieved_GBs': round(gbs, 1), 'peak_GBs': pk, 'frac': round(gbs / pk, 3)}), flush=True)
+                rec = {'op': name, 'dtype': str(dtype).replace('torch.', ''), 'layout': layout, 'shape': list(x.shape), 'out': list(y.shape),
+                       'ours_ms': round(ms, 4), 'algorithmic_GB': round(nbytes / 1e9, 3), 'achieved_GBs': round(gbs, 1), 'peak_GBs': pk, 'frac': round(gbs / pk, 3)}
+                if refops is not None:              # the reference's own sm_100a-compiled plugin on the same tensor, same call
+                    try:
+                        with torch.no_grad():
+                            rms, ry = timeit(lambda: fn(refops), reps=5, warm=2)
+                        rec.update(ref_plugin_ms=round(rms, 4), speedup_vs_ref_plugin=round(rms / ms, 2),
+                                   max_abs_diff_vs_ref_plugin=float((ry.float() - y.float()).abs().max()))
+                        del ry
+                    except Exception as e:      # noqa
+                        rec.update(ref_plugin_error=str(e)[:160])
+                print(json.dumps(rec), flush=True)
                 del y
 
     # ---- the fused forms on the shapes of the synthesis step (NHWC fp32, batch 8): algorithmic bytes = every tensor once
