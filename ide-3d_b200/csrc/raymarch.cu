@@ -11,6 +11,8 @@
 //
 // Mapping: persistent blocks of 8 warps; a block walks 4x2 pixel tiles (neighbouring rays share the
 // yz / xz plane lines in L1), one warp per ray, 32 samples per chunk, compositing carried in registers.
+#include <stdlib.h>
+
 #include "raymarch_common.cuh"
 
 namespace ide3d {
@@ -190,6 +192,7 @@ static int launch_raymarch(const RayArgs& a, cudaStream_t st) {
 }
 
 int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaStream_t st);   // raymarch_tc.cu
+namespace v1 { int launch_raymarch_tc_v1(const ide3d_raymarch_params* p, bool channels_last, cudaStream_t st); }   // raymarch_tc_v1.cu (round-1 kernel, A/B only)
 
 }  // namespace ide3d
 
@@ -224,7 +227,9 @@ extern "C" int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t
     IDE3D_REQUIRE(p->precision >= IDE3D_PRECISION_AUTO && p->precision <= IDE3D_PRECISION_TC, "raymarch: bad precision");
     const bool planes_cl = is_channels_last(p->tex) && is_channels_last(p->seg);
     if (p->precision != IDE3D_PRECISION_FP32) {
-        const int rc_tc = launch_raymarch_tc(p, planes_cl, (cudaStream_t)stream);
+        const char* v1 = getenv("IDE3D_TC_V1");
+        const int rc_tc = (v1 && v1[0] == '1') ? v1::launch_raymarch_tc_v1(p, planes_cl, (cudaStream_t)stream)
+                                               : launch_raymarch_tc(p, planes_cl, (cudaStream_t)stream);
         if (rc_tc != IDE3D_UNSUPPORTED || p->precision == IDE3D_PRECISION_TC) return rc_tc;
     }
     const int kind = classify_decoder(p->dec);

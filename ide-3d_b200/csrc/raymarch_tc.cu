@@ -1,29 +1,28 @@
-// Fused volume renderer, tensor-core decoder: the same chain as raymarch.cu (rays -> jitter -> cam2world -> 2x tri-plane
-// gather -> decoder MLP -> alpha compositing) with the per-sample MLP executed as tcgen05.mma tiles.
+// Fused volume renderer, tensor-core decoder (round-2 design): rays -> jitter -> cam2world -> 2x tri-plane gather -> decoder MLP
+// -> alpha compositing in ONE kernel, no per-sample intermediate in HBM (training/volumetric_rendering.py:34-136,
+// dnnlib/util.py:580-617 and the generator's decoder in one pass).
 //
-//   tile   = 128 samples (M = 128): 4 x 32 consecutive samples of 4 neighbouring rays (2x2 pixels)
+//   unit   = 4x4 neighbouring rays, marched front to back; tile = 8 consecutive depth samples of the 16 rays = 128 rows (M = 128)
+//            row r: warp quarter r/32 = pixel row of the unit, lane = (pixel column)*8 + depth index   -> the 8 samples of a ray
+//            sit in 8 adjacent lanes (compositing = 8-lane segmented product), rays that share a plane row / column share texels
 //   A      = gathered features [128 x 64] (texture 0..31 | shape 32..63), bf16 hi + lo, K-major, 128B-swizzled smem rows
-//   layer 1: D1[128 x 64] = A . W1_blk^T      accumulators in TMEM (fp32)
-//   epilog : tcgen05.ld D1 -> + b1 -> softplus -> bf16 hi + lo -> A2 [128 x 64] in smem
-//   layer 2: D2[128 x n]  (+)= A2 . W2_blk^T  for the output-column range the block feeds
-//   final  : tcgen05.ld D2 -> + b2 -> sigma -> warp product scan -> weighted accumulation in registers
-// The decoder is processed in hidden blocks of 64 units (three-head decoder: one block per head; dense decoders: HID/64
-// blocks).  Zero blocks of W1 (a head reads only the texture or only the shape half) and of W2 (a head feeds only its
-// own output columns) are skipped by construction of the MMA program.
+//   layer 1: D1[128 x 64] per hidden block = A . W1_blk^T, fp32 accumulators in TMEM
+//   epilog : tcgen05.ld D1 -> + b1 -> softplus -> bf16 hi / lo -> tcgen05.st back INTO THE SAME TMEM COLUMNS (16 fp32 columns
+//            become 8 packed hi + 8 packed lo columns: one K = 16 step)
+//   layer 2: D2[128 x n] (+)= A2 . W2_blk^T with the A operand read FROM TMEM (tcgen05.mma [d], [a_tmem], b_desc): no shared-memory
+//            round trip, no proxy fence, no block-wide barrier between the two layers
+//   final  : tcgen05.ld D2 -> + b2 -> sigma -> alpha -> 8-lane product scan (+ carried transmittance) -> weighted accumulation in
+//            registers; one 8-lane reduction per ray at the end of the march
+// Every product is bf16 hi*hi + hi*lo + lo*hi with fp32 accumulation ("bf16x3": 16 mantissa bits per operand).
 //
-// Precision: every product is evaluated as hi*hi + hi*lo + lo*hi with bf16 operands and fp32 accumulation ("bf16x3"):
-// operands carry 16 mantissa bits, the dropped lo*lo term is 2^-16 relative.  Measured against the fp32 oracle in
-// tests/test_gpu_renderer.py (tolerance stated there).
-//
-// Warp-specialised, one persistent CTA per SM (512 threads):
-//   warpgroups 0-1 (8 warps) consumers: wait for a full A stage, issue the UMMAs (one elected thread), run the softplus and
-//                          compositing epilogues out of TMEM.  Warp w and w+4 share TMEM lanes 32*(w%4).. and split the
-//                          columns: in the softplus epilogue each takes 32 of the 64 hidden units; in the final epilogue the
-//                          lower warp takes sigma + the 19 semantic logits (and computes the compositing weight), the upper
-//                          warp the 32 colour features (weight handed over through shared memory).  104 registers/thread.
-//   warpgroups 2-3 (8 warps) producers: compute sample positions and gather features into a 3-stage ring of A tiles
-//                          (152 registers/thread, 24 x LDG.128 in flight per lane); mbarrier full/empty hand-off, the "empty"
-//                          arrive is the tcgen05.commit of the last MMA that reads the stage.
+// Warp-specialised persistent CTA, 640 threads, one CTA per SM:
+//   warps 0-3 / 4-7    two consumer GROUPS; a group owns 256 TMEM columns (D1 3x64 + D2 64) and marches its own units, so the MMA /
+//                      commit latency of one group's tile is covered by the softplus / compositing work of the other group;
+//                      lane 0 of a group's first warp issues its MMAs
+//   warps 8-19         producers, three teams of four warps; a team fills one 32 KB A stage (a tile) at a time: sample positions,
+//                      per-axis bilinear footprints (once per sample, by the lane that owns it), 8 lanes per texel x LDG.128,
+//                      blend, bf16 split, swizzled st.shared; mbarrier full / empty ring, "empty" = tcgen05.commit of layer 1
+// Shared memory: compacted weight tiles (52 KB for the three-head decoder) + kStages x 32 KB, so that 64+ KB stay L1 for the gather.
 #include <stdlib.h>
 
 #include "raymarch_common.cuh"
@@ -31,28 +30,31 @@
 
 namespace ide3d {
 
-constexpr int kTcConsumerThreads = 256;                       // 8 warps: (TMEM lane quarter) x (column half)
-constexpr int kTcProducerWarps = 8;
-constexpr int kTcThreads = kTcConsumerThreads + kTcProducerWarps * 32;
-constexpr int kTcStages = 3;
+constexpr int kGroups = 2;
+constexpr int kConsumerWarps = 4 * kGroups;
+constexpr int kMaxTeams = 3;                                             // producer teams (template parameter TEAMS = 2 or 3); a team owns one
+                                                                         // A stage and refills it as soon as layer 1 has read it
 constexpr int kTcMaxBlocks = 3;
-constexpr int kTileBytes = 128 * 128;                         // [128 rows x 64 bf16]
-constexpr int kWTileBytes = 64 * 128;                         // [64 rows x 64 bf16]
-constexpr int kTmemCols = 256;                                // D1 3 x 64 (one per hidden block) + D2 64
-
-// ---- shared memory map (bytes) ----
-constexpr int kSmW = 0;                                       // per block: W1 hi, W1 lo, W2 hi, W2 lo (8 KB each)
-constexpr int kSmA2 = kSmW + kTcMaxBlocks * 4 * kWTileBytes;                // 98304: A2 hi, A2 lo
-constexpr int kSmStage = kSmA2 + 2 * kTileBytes;                             // 131072: kTcStages x (A hi, A lo)
-constexpr int kSmMisc = kSmStage + kTcStages * 2 * kTileBytes;              // 229376
-constexpr int kSmMiscBytes = (kTcMaxBlocks * 64 + 64 + 128 + 8) * 4 + 128;  // b1[192], b2[64], w hand-off[128], wsum[4+4], mbarriers, tmem ptr
-constexpr int kTcSmemBytes = kSmMisc + kSmMiscBytes + 1024;                 // + slack for the 1024-byte alignment
+constexpr int kTileBytes = 128 * 128;                                    // [128 rows x 64 bf16]
+constexpr int kStageBytes = 2 * kTileBytes;                              // hi + lo
+constexpr int kGroupCols = 256;                                          // TMEM columns per group: D1 3 x 64, D2 64
+constexpr int kD2Col = 64 * kTcMaxBlocks;
+constexpr int kUnitW = 4, kUnitH = 4, kTileDepth = 8;
+// register split (setmaxnreg): TEAMS = 3: 256 x 112 + 384 x 96 = 65536;  TEAMS = 2: 256 x 120 + 256 x 136 = 65536
+template <int TEAMS> struct TcCfg {
+    static constexpr int kThreads = 32 * (kConsumerWarps + 4 * TEAMS);
+    static constexpr int kConsumerRegs = (TEAMS == 3) ? 112 : 120;
+    static constexpr int kProducerRegs = (TEAMS == 3) ? 96 : 136;
+    static constexpr int kBaseRegs = (TEAMS == 3) ? 96 : 128;           // what __launch_bounds__(kThreads, 1) compiles to
+};
 
 struct TcRun { int n0, n, accum; };
 struct TcBlock {
     const float* w1; int w1_ld, k0, kcount;        // W1 rows of this hidden block; inputs land at A columns [k0, k0+kcount)
     const float* b1;
     const float* w2; int w2_ld, out0, outc;        // W2[out, hidden cols of this block]; rows feed outputs [out0, out0+outc)
+    int w1_off;                                    // byte offset of the [64 x 64] W1 tile inside a weight part (shared by two 32-input blocks)
+    int w2_off, w2_row0;                           // byte offset of the W2 row block; its first row is output column w2_row0
     int nruns;
     TcRun runs[4];                                 // layer-2 MMAs: D2 columns [n0, n0+n), accumulate or overwrite
 };
@@ -60,6 +62,7 @@ struct TcProgram {
     int nblocks;
     TcBlock blk[kTcMaxBlocks];
     unsigned written;                              // bit g: D2 columns [16g, 16g+16) are produced by some block
+    int wpart;                                     // bytes of one weight part (hi or lo), multiple of 1024
 };
 
 struct TcArgs {
@@ -76,12 +79,12 @@ struct TcArgs {
     float max_depth, noise_std;
     const float* noise;
     float *out_feat, *out_depth, *out_weights;
-    int tiles_x, tiles_y;
-    int debug;                                     // IDE3D_TC_DEBUG: 1 = producers skip the gather, 2 = consumer skips the decoder (timing experiments only)
+    int units_x, units_y, num_units, tiles_per_unit;
+    int ray_major;                                 // gather instruction = 4 depth-consecutive samples of one ray (1) or 4 x-adjacent rays (0)
 };
 
-// log2(1 + 2^t): the hidden softplus in base-2 units (see the weight set-up).  ex2 of the clamped argument cannot overflow;
-// for t >= 24 the sum rounds to 2^t and lg2 returns t itself, and max(., t) keeps t beyond the clamp (the function is >= t).
+// log2(1 + 2^t): the hidden softplus in base-2 units (log2e folded into W1 / b1, ln2 into W2 at set-up).  ex2 of the clamped
+// argument cannot overflow; for t >= 24 the sum rounds to 2^t and lg2 returns t itself, max(., t) keeps t beyond the clamp.
 __device__ __forceinline__ float softplus2(float t) {
     float e, l;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(t, 126.f)));
@@ -89,26 +92,44 @@ __device__ __forceinline__ float softplus2(float t) {
     return fmaxf(l, t);
 }
 
-// write element (row, k) of a [rows x 64] bf16 swizzle-128B tile
 __device__ __forceinline__ void tile_store_bf16(unsigned char* tile, int row, int k, __nv_bfloat16 v) {
     *reinterpret_cast<__nv_bfloat16*>(tile + tc::sw128_offset(row, k >> 3) + (k & 7) * 2) = v;
 }
 
-// per-ray constants shared by producer and consumer code
+// ---------------------------------------------------------------------------------------------------------------------------
+// work decomposition shared by producers and consumers
+struct Schedule {
+    int cnt0, cnt1;          // units of the two groups of this CTA
+    int tiles0, tiles1;      // tiles of the two groups
+    int m;                   // tiles of the shorter group: sequence numbers below 2m alternate between the groups
+};
+__device__ __forceinline__ Schedule make_schedule(const TcArgs& a) {
+    Schedule s;
+    const int stride = kGroups * gridDim.x;
+    const int f0 = blockIdx.x * kGroups, f1 = f0 + 1;
+    s.cnt0 = (f0 < a.num_units) ? (a.num_units - f0 + stride - 1) / stride : 0;
+    s.cnt1 = (f1 < a.num_units) ? (a.num_units - f1 + stride - 1) / stride : 0;
+    s.tiles0 = s.cnt0 * a.tiles_per_unit;
+    s.tiles1 = s.cnt1 * a.tiles_per_unit;
+    s.m = min(s.tiles0, s.tiles1);                       // group 0 never has fewer units than group 1
+    return s;
+}
+__device__ __forceinline__ int seq_of(const Schedule& s, int g, int t) { return (t < s.m) ? 2 * t + g : 2 * s.m + (t - s.m); }
+
+// per-ray constants
 struct RaySetup {
     int n, ray;
     bool ok;
     float dx, dy, dz, dnorm, spacing;
-    float m00, m01, m02, m03, m10, m11, m12, m13, m20, m21, m22, m23;
     long long sample_base;
 };
-__device__ __forceinline__ RaySetup ray_setup(const TcArgs& a, int ptile, int quarter) {
+__device__ __forceinline__ RaySetup ray_setup(const TcArgs& a, int unit, int rx, int ry) {
     RaySetup r;
-    const int tiles_per_frame = a.tiles_x * a.tiles_y;
-    r.n = ptile / tiles_per_frame;
-    const int t = ptile - r.n * tiles_per_frame;
-    const int px = (t % a.tiles_x) * 2 + (quarter & 1);
-    const int py = (t / a.tiles_x) * 2 + (quarter >> 1);
+    const int per_frame = a.units_x * a.units_y;
+    r.n = unit / per_frame;
+    const int t = unit - r.n * per_frame;
+    const int px = (t % a.units_x) * kUnitW + rx;
+    const int py = (t / a.units_x) * kUnitH + ry;
     r.ok = (px < a.res_w) && (py < a.res_h);
     r.ray = r.ok ? py * a.res_w + px : 0;
     const float x = linspace_at(-1.f, 1.f, a.res_w, px);
@@ -116,10 +137,6 @@ __device__ __forceinline__ RaySetup ray_setup(const TcArgs& a, int ptile, int qu
     const float inv = 1.f / sqrtf(x * x + y * y + a.cam_z * a.cam_z);
     r.dx = x * inv; r.dy = y * inv; r.dz = a.cam_z * inv;
     r.dnorm = sqrtf(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
-    const float* M = a.cam2world + r.n * 16;
-    r.m00 = M[0]; r.m01 = M[1]; r.m02 = M[2]; r.m03 = M[3];
-    r.m10 = M[4]; r.m11 = M[5]; r.m12 = M[6]; r.m13 = M[7];
-    r.m20 = M[8]; r.m21 = M[9]; r.m22 = M[10]; r.m23 = M[11];
     const int S = a.steps;
     r.spacing = (S > 1) ? linspace_at(a.ray_start, a.ray_end, S, 1) - linspace_at(a.ray_start, a.ray_end, S, 0) : 0.f;
     r.sample_base = ((long long)r.n * (a.res_w * a.res_h) + r.ray) * S;
@@ -141,37 +158,123 @@ __device__ __forceinline__ void sample_depths(const TcArgs& a, const RaySetup& r
     }
 }
 
-__global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs a) {
+// one tri-plane's contribution to 4 channels of one sample: 12 LDG.128 in flight, then the blend (plane by plane, taps in the
+// order (col lo,row lo) (col hi,row lo) (col lo,row hi) (col hi,row hi) -- the arithmetic of gather_chunk_axes)
+// Offsets are 32-bit BYTE offsets (tap = row role + column role + plane * 128 B; the lane's channel quad is already folded into the
+// column roles), added to a 64-bit per-frame base: 3 integer instructions per load.
+__device__ __forceinline__ float4 ldg_at(const char* __restrict__ base, unsigned byte_off) {
+    return __ldg(reinterpret_cast<const float4*>(base + byte_off));
+}
+__device__ __forceinline__ void gather12(const char* __restrict__ base, const AxisTaps& X, const AxisTaps& Yr, const AxisTaps& Yc,
+                                         const AxisTaps& Z, float (&out)[4]) {
+    float4 v[12];
+#define IDE3D_LD(k, C, R)                                                                                         \
+    v[4 * k + 0] = ldg_at(base, (unsigned)(R.lo + C.lo + k * (kFeat * 4))); v[4 * k + 1] = ldg_at(base, (unsigned)(R.lo + C.hi + k * (kFeat * 4))); \
+    v[4 * k + 2] = ldg_at(base, (unsigned)(R.hi + C.lo + k * (kFeat * 4))); v[4 * k + 3] = ldg_at(base, (unsigned)(R.hi + C.hi + k * (kFeat * 4)));
+    IDE3D_LD(0, X, Yr)
+    IDE3D_LD(1, Yc, Z)
+    IDE3D_LD(2, X, Z)
+#undef IDE3D_LD
+    out[0] = out[1] = out[2] = out[3] = 0.f;
+#define IDE3D_BLEND(k, C, R)                                                                                      \
+    {                                                                                                             \
+        const float w4[4] = {C.wlo * R.wlo, C.whi * R.wlo, C.wlo * R.whi, C.whi * R.whi};                         \
+        float p[4] = {0.f, 0.f, 0.f, 0.f};                                                                        \
+        _Pragma("unroll") for (int tap = 0; tap < 4; ++tap) {                                                     \
+            const float4 t4 = v[k * 4 + tap];                                                                     \
+            const float w_ = w4[tap];                                                                             \
+            p[0] += t4.x * w_; p[1] += t4.y * w_; p[2] += t4.z * w_; p[3] += t4.w * w_;                           \
+        }                                                                                                         \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) out[j] += p[j];                                             \
+    }
+    IDE3D_BLEND(0, X, Yr)
+    IDE3D_BLEND(1, Yc, Z)
+    IDE3D_BLEND(2, X, Z)
+#undef IDE3D_BLEND
+}
+
+// both tri-planes of one sample in one batch: 24 LDG.128 in flight (the 2-team variant has the registers for it)
+__device__ __forceinline__ void gather24(const char* __restrict__ tb, const char* __restrict__ sb, const AxisTaps& X, const AxisTaps& Yr,
+                                         const AxisTaps& Yc, const AxisTaps& Z, float (&at)[4], float (&as)[4]) {
+    float4 v[12], u[12];
+#define IDE3D_LD(k, C, R)                                                                                         \
+    {                                                                                                             \
+        const unsigned o0 = R.lo + C.lo + k * (kFeat * 4), o1 = R.lo + C.hi + k * (kFeat * 4);                    \
+        const unsigned o2 = R.hi + C.lo + k * (kFeat * 4), o3 = R.hi + C.hi + k * (kFeat * 4);                    \
+        v[4 * k + 0] = ldg_at(tb, o0); v[4 * k + 1] = ldg_at(tb, o1); v[4 * k + 2] = ldg_at(tb, o2); v[4 * k + 3] = ldg_at(tb, o3); \
+        u[4 * k + 0] = ldg_at(sb, o0); u[4 * k + 1] = ldg_at(sb, o1); u[4 * k + 2] = ldg_at(sb, o2); u[4 * k + 3] = ldg_at(sb, o3); \
+    }
+    IDE3D_LD(0, X, Yr)
+    IDE3D_LD(1, Yc, Z)
+    IDE3D_LD(2, X, Z)
+#undef IDE3D_LD
+    at[0] = at[1] = at[2] = at[3] = 0.f;
+    as[0] = as[1] = as[2] = as[3] = 0.f;
+#define IDE3D_BLEND(k, C, R)                                                                                      \
+    {                                                                                                             \
+        const float w4[4] = {C.wlo * R.wlo, C.whi * R.wlo, C.wlo * R.whi, C.whi * R.whi};                         \
+        float p[4] = {0.f, 0.f, 0.f, 0.f}, r[4] = {0.f, 0.f, 0.f, 0.f};                                           \
+        _Pragma("unroll") for (int tap = 0; tap < 4; ++tap) {                                                     \
+            const float4 t4 = v[k * 4 + tap], s4 = u[k * 4 + tap];                                                \
+            const float w_ = w4[tap];                                                                             \
+            p[0] += t4.x * w_; p[1] += t4.y * w_; p[2] += t4.z * w_; p[3] += t4.w * w_;                           \
+            r[0] += s4.x * w_; r[1] += s4.y * w_; r[2] += s4.z * w_; r[3] += s4.w * w_;                           \
+        }                                                                                                         \
+        _Pragma("unroll") for (int j = 0; j < 4; ++j) { at[j] += p[j]; as[j] += r[j]; }                           \
+    }
+    IDE3D_BLEND(0, X, Yr)
+    IDE3D_BLEND(1, Yc, Z)
+    IDE3D_BLEND(2, X, Z)
+#undef IDE3D_BLEND
+}
+
+__device__ __forceinline__ AxisTaps shfl_taps(const AxisTaps& t, int src) {
+    AxisTaps r;
+    r.lo = __shfl_sync(kFull, t.lo, src); r.hi = __shfl_sync(kFull, t.hi, src);
+    r.wlo = __shfl_sync(kFull, t.wlo, src); r.whi = __shfl_sync(kFull, t.whi, src);
+    return r;
+}
+
+template <int TEAMS>
+__global__ void __launch_bounds__(TcCfg<TEAMS>::kThreads, 1) raymarch_tc_kernel(const TcArgs a) {
+    constexpr int kStages = TEAMS, kTeams = TEAMS, kTcThreads = TcCfg<TEAMS>::kThreads;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* b1s = reinterpret_cast<float*>(smem + kSmMisc);
-    float* b2s = b1s + kTcMaxBlocks * 64;
-    float* wbuf = b2s + 64;                                              // [128] compositing weight of each row (half 0 -> half 1)
-    float* wsumbuf = wbuf + 128;                                         // [4] weights_sum of the 4 rays
-    uint64_t* bar_full = reinterpret_cast<uint64_t*>(wsumbuf + 8);      // [kTcStages] producers -> consumer
-    uint64_t* bar_empty = bar_full + kTcStages;                        // [kTcStages] consumer (tcgen05.commit) -> producers
-    uint64_t* bar_mma = bar_empty + kTcStages;                         // consumer-internal: MMA batch done
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_mma + 1);
+    const TcProgram& P = a.prog;
+    unsigned char* w_hi = smem;
+    unsigned char* w_lo = smem + P.wpart;
+    unsigned char* stage_base = smem + 2 * P.wpart;
+    unsigned char* misc = stage_base + kStages * kStageBytes;
+    float* b1s = reinterpret_cast<float*>(misc);                         // [3 x 64] hidden biases (x log2e)
+    float* b2s = b1s + kTcMaxBlocks * 64;                                 // [64] output biases
+    uint64_t* bar_full = reinterpret_cast<uint64_t*>(b2s + 64);         // [kStages] producer team -> consumers
+    uint64_t* bar_empty = bar_full + kMaxTeams;                      // [kStages] layer-1 commit -> producers
+    uint64_t* bar_d1 = bar_empty + kMaxTeams;                        // [kGroups] layer 1 done
+    uint64_t* bar_a2 = bar_d1 + kGroups;                                // [kGroups][kTcMaxBlocks] A2 of a hidden block is in TMEM (4 warp arrivals)
+    uint64_t* bar_d2 = bar_a2 + kGroups * kTcMaxBlocks;                 // [kGroups] layer 2 done
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_d2 + kGroups);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const TcProgram& P = a.prog;
 
-    // ---------------- one-time setup: weights -> bf16 hi/lo swizzled tiles, biases, barriers, TMEM
+    // ---------------- one-time setup: weights -> bf16 hi/lo swizzled tiles (compacted), biases, barriers, TMEM
+    for (int i = tid; i < (2 * P.wpart) / 16; i += kTcThreads) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
     for (int i = tid; i < P.nblocks * 64 * 64; i += kTcThreads) {
         const int b = i >> 12, j = (i >> 6) & 63, k = i & 63;
         const TcBlock& B = P.blk[b];
-        unsigned char* base = smem + kSmW + b * 4 * kWTileBytes;
-        // The hidden activation is evaluated in base 2: softplus(x) = ln2 * log2(1 + 2^(x*log2e)).  log2e is folded into W1 / b1
-        // and ln2 into W2 here, once, so the per-sample epilogue is add-bias, ex2, +1, lg2 (softplus2 below).
-        const float v1 = (k >= B.k0 && k < B.k0 + B.kcount) ? B.w1[j * B.w1_ld + (k - B.k0)] * 1.4426950408889634f : 0.f;   // W1[hidden j][input k]
-        const float v2 = (j >= B.out0 && j < B.out0 + B.outc) ? B.w2[(j - B.out0) * B.w2_ld + k] * 0.6931471805599453f : 0.f; // W2[output j][hidden k]
         __nv_bfloat16 hi, lo;
-        tc::split_bf16(v1, hi, lo);
-        tile_store_bf16(base, j, k, hi);
-        tile_store_bf16(base + kWTileBytes, j, k, lo);
-        tc::split_bf16(v2, hi, lo);
-        tile_store_bf16(base + 2 * kWTileBytes, j, k, hi);
-        tile_store_bf16(base + 3 * kWTileBytes, j, k, lo);
+        // hidden activation in base 2: softplus(x) = ln2 * log2(1 + 2^(x*log2e)); log2e goes into W1 / b1, ln2 into W2, once
+        if (k < B.kcount) {                                                  // W1[hidden j][input k] -> column k0 + k
+            tc::split_bf16(B.w1[j * B.w1_ld + k] * 1.4426950408889634f, hi, lo);
+            tile_store_bf16(w_hi + B.w1_off, j, B.k0 + k, hi);
+            tile_store_bf16(w_lo + B.w1_off, j, B.k0 + k, lo);
+        }
+        const int oc = B.w2_row0 + j;                                        // W2[output oc][hidden k] -> row j of the row block
+        if (oc >= B.out0 && oc < B.out0 + B.outc) {
+            tc::split_bf16(B.w2[(oc - B.out0) * B.w2_ld + k] * 0.6931471805599453f, hi, lo);
+            tile_store_bf16(w_hi + B.w2_off, j, k, hi);
+            tile_store_bf16(w_lo + B.w2_off, j, k, lo);
+        }
     }
     for (int i = tid; i < kTcMaxBlocks * 64; i += kTcThreads) b1s[i] = (i < P.nblocks * 64) ? P.blk[i >> 6].b1[i & 63] * 1.4426950408889634f : 0.f;
     if (tid < 64) {
@@ -183,11 +286,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
         b2s[tid] = v;
     }
     if (tid == 0) {
-        for (int i = 0; i < kTcStages; ++i) { tc::mbar_init(&bar_full[i], 4); tc::mbar_init(&bar_empty[i], 1); }
-        tc::mbar_init(bar_mma, 1);
+        for (int i = 0; i < kStages; ++i) { tc::mbar_init(&bar_full[i], 4); tc::mbar_init(&bar_empty[i], 1); }
+        for (int g = 0; g < kGroups; ++g) { tc::mbar_init(&bar_d1[g], 1); tc::mbar_init(&bar_d2[g], 1); }
+        for (int i = 0; i < kGroups * kTcMaxBlocks; ++i) tc::mbar_init(&bar_a2[i], 4);
         tc::fence_mbar_init();
     }
-    if (warp == 0) tc::tmem_alloc(tmem_slot, kTmemCols);
+    if (warp == 0) tc::tmem_alloc(tmem_slot, kGroups * kGroupCols);
     tc::fence_async_smem();
     tc::tc_fence_before();
     __syncthreads();
@@ -195,260 +299,282 @@ __global__ void __launch_bounds__(kTcThreads, 1) raymarch_tc_kernel(const TcArgs
     const uint32_t tmem_base = *tmem_slot;
 
     const int S = a.steps;
-    const int num_ptiles = a.tiles_x * a.tiles_y * a.n;
-    const int chunks = (S + 31) >> 5;
+    const Schedule sch = make_schedule(a);
+    const int unit_stride = kGroups * gridDim.x;
 
-    if (warp >= 8) {
+    if (warp >= kConsumerWarps) {
         // =========================================================================== producers
-        tc::setmaxnreg_inc<152>();
-        const int pw = warp - 8, pg = pw >> 2, quarter = pw & 3;
-        int q = 0;
-        for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
-            const RaySetup r = ray_setup(a, pt, quarter);
-            for (int ch = 0; ch < chunks; ++ch, ++q) {
-                if ((q & 1) != pg) continue;
-                const int stage = q % kTcStages, use = q / kTcStages;
-                tc::mbar_wait(&bar_empty[stage], (use + 1) & 1);             // first use passes immediately
-                const int s = ch * 32 + lane;
-                const bool live = r.ok && (s < S);
-                float cx = 4.f, cy = 4.f, cz = 4.f;
-                if (live) {
-                    float z0, off0, z1;
-                    sample_depths(a, r, s, z0, off0, z1);
-                    const float pcx = r.dx * z0 + off0 * r.dx, pcy = r.dy * z0 + off0 * r.dy, pcz = r.dz * z0 + off0 * r.dz;
-                    cx = (r.m00 * pcx + r.m01 * pcy + r.m02 * pcz + r.m03) * a.box_scale;
-                    cy = (r.m10 * pcx + r.m11 * pcy + r.m12 * pcz + r.m13) * a.box_scale;
-                    cz = (r.m20 * pcx + r.m21 * pcy + r.m22 * pcz + r.m23) * a.box_scale;
-                }
-                unsigned char* a_hi = smem + kSmStage + stage * 2 * kTileBytes;
-                unsigned char* a_lo = a_hi + kTileBytes;
-                if (a.debug != 1) gather_chunk_axes(a.tex, a.seg, r.n, cx, cy, cz, lane,
-                                      [&](int src, int qq, const float (&at)[4], const float (&as)[4]) {
-                                          const int row = quarter * 32 + src;
-                                          __nv_bfloat16 h[4], l[4];
-#pragma unroll
-                                          for (int j = 0; j < 4; ++j) tc::split_bf16(at[j], h[j], l[j]);
-                                          uint32_t o = tc::sw128_offset(row, qq >> 1) + (qq & 1) * 8;
-                                          *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
-                                          *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
-#pragma unroll
-                                          for (int j = 0; j < 4; ++j) tc::split_bf16(as[j], h[j], l[j]);
-                                          o = tc::sw128_offset(row, 4 + (qq >> 1)) + (qq & 1) * 8;
-                                          *reinterpret_cast<uint2*>(a_hi + o) = make_uint2(tc::pack_bf16(h[0], h[1]), tc::pack_bf16(h[2], h[3]));
-                                          *reinterpret_cast<uint2*>(a_lo + o) = make_uint2(tc::pack_bf16(l[0], l[1]), tc::pack_bf16(l[2], l[3]));
-                                      });
-                tc::fence_async_smem();                                      // my generic-proxy stores -> async proxy (UMMA)
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&bar_full[stage]);
+        if constexpr (TcCfg<TEAMS>::kProducerRegs < TcCfg<TEAMS>::kBaseRegs) tc::setmaxnreg_dec<TcCfg<TEAMS>::kProducerRegs>();
+        else if constexpr (TcCfg<TEAMS>::kProducerRegs > TcCfg<TEAMS>::kBaseRegs) tc::setmaxnreg_inc<TcCfg<TEAMS>::kProducerRegs>();
+        const int pw = warp - kConsumerWarps, team = pw >> 2, qw = pw & 3;
+        const int total = sch.tiles0 + sch.tiles1;
+        const int shb = (int)(a.tex.sh * 4), swb = (int)(a.tex.sw * 4);     // strides in bytes (32-bit: checked by the launcher)
+        const int W = a.tex.w, H = a.tex.h;
+        const int q4 = lane & 7, grp = lane >> 3;
+        for (int seq = team; seq < total; seq += kTeams) {
+            int g, t;
+            if (seq < 2 * sch.m) { g = seq & 1; t = seq >> 1; } else { g = 0; t = sch.m + (seq - 2 * sch.m); }
+            const int ui = t / a.tiles_per_unit, step = t - ui * a.tiles_per_unit;
+            const int unit = blockIdx.x * kGroups + g + ui * unit_stride;
+            const RaySetup r = ray_setup(a, unit, lane >> 3, qw);
+            const int s = step * kTileDepth + (lane & 7);
+            const bool live = r.ok && (s < S);
+            float cx = 4.f, cy = 4.f, cz = 4.f;                                // far outside the planes: every tap gets weight 0
+            if (live) {
+                const float* M = a.cam2world + r.n * 16;
+                float z0, off0, z1;
+                sample_depths(a, r, s, z0, off0, z1);
+                const float pcx = r.dx * z0 + off0 * r.dx, pcy = r.dy * z0 + off0 * r.dy, pcz = r.dz * z0 + off0 * r.dz;
+                cx = (M[0] * pcx + M[1] * pcy + M[2] * pcz + M[3]) * a.box_scale;
+                cy = (M[4] * pcx + M[5] * pcy + M[6] * pcz + M[7]) * a.box_scale;
+                cz = (M[8] * pcx + M[9] * pcy + M[10] * pcz + M[11]) * a.box_scale;
             }
+            // bilinear footprint per axis role, computed ONCE per sample by its own lane (dnnlib/util.py:589-596: plane 0 = (x,y),
+            // plane 1 = (y,z), plane 2 = (x,z)); the 8 lanes that fetch a sample's texels receive it by shuffle
+            const AxisFoot fx = axis_foot(cx, W), fyr = axis_foot(cy, H), fyc = axis_foot(cy, W), fz = axis_foot(cz, H);
+            const AxisTaps mX = axis_taps(fx.i0, fx.f, W, swb), mYr = axis_taps(fyr.i0, fyr.f, H, shb);
+            const AxisTaps mYc = axis_taps(fyc.i0, fyc.f, W, swb), mZ = axis_taps(fz.i0, fz.f, H, shb);
+            const char* tb = reinterpret_cast<const char*>(a.tex.base + (long long)r.n * a.tex.sn);
+            const char* sb = reinterpret_cast<const char*>(a.seg.base + (long long)r.n * a.seg.sn);
+
+            const int stage = seq % kStages, use = seq / kStages;
+            unsigned char* a_hi = stage_base + stage * kStageBytes;
+            unsigned char* a_lo = a_hi + kTileBytes;
+#pragma unroll 1
+            for (int it = 0; it < 8; ++it) {
+                const int src = a.ray_major ? (it * 4 + grp) : (grp * 8 + it);
+                AxisTaps X = shfl_taps(mX, src), Yc = shfl_taps(mYc, src);
+                const AxisTaps Yr = shfl_taps(mYr, src), Z = shfl_taps(mZ, src);
+                X.lo += q4 * 16; X.hi += q4 * 16; Yc.lo += q4 * 16; Yc.hi += q4 * 16;      // this lane's channel quad (every tap has one column role)
+                const int row = qw * 32 + src;
+                const uint32_t o_tex = tc::sw128_offset(row, q4 >> 1) + (q4 & 1) * 8;
+                const uint32_t o_seg = tc::sw128_offset(row, 4 + (q4 >> 1)) + (q4 & 1) * 8;
+                float f[4], f2[4];
+                uint2 hi, lo;
+                if constexpr (TEAMS == 2) gather24(tb, sb, X, Yr, Yc, Z, f, f2);    // 24 loads in flight per lane
+                else gather12(tb, X, Yr, Yc, Z, f);                                  // 12, then the shape tri-plane below
+                tc::split4_bf16(f, hi, lo);
+                // the stage is needed only now: the first gather of the tile overlaps the wait for layer 1 of the tile that used it before
+                if (it == 0) tc::mbar_wait(&bar_empty[stage], (use + 1) & 1);       // first use passes immediately
+                *reinterpret_cast<uint2*>(a_hi + o_tex) = hi;
+                *reinterpret_cast<uint2*>(a_lo + o_tex) = lo;
+                if constexpr (TEAMS != 2) gather12(sb, X, Yr, Yc, Z, f2);
+                tc::split4_bf16(f2, hi, lo);
+                *reinterpret_cast<uint2*>(a_hi + o_seg) = hi;
+                *reinterpret_cast<uint2*>(a_lo + o_seg) = lo;
+            }
+            tc::fence_async_smem();                                            // my generic-proxy stores -> async proxy (UMMA)
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&bar_full[stage]);
         }
     } else {
         // =========================================================================== consumers
-        tc::setmaxnreg_dec<104>();
-        const int wg = warp & 3, half = warp >> 2;                 // TMEM lane quarter (= ray of the 2x2 tile), column half
-        const uint32_t d1_col = tmem_base, d2_col = tmem_base + 64 * kTcMaxBlocks;
-        const uint32_t lane_sel = (uint32_t)(wg * 32) << 16;
-        unsigned char* a2_hi = smem + kSmA2;
-        unsigned char* a2_lo = a2_hi + kTileBytes;
-        const uint32_t a2_hi_u = tc::smem_u32(a2_hi), a2_lo_u = tc::smem_u32(a2_lo);
-        const uint32_t w_u = tc::smem_u32(smem + kSmW);
-        const uint32_t stage_u = tc::smem_u32(smem + kSmStage);
-        const bool issuer = (warp == 0 && lane == 0);
-        const int row = wg * 32 + lane;
-        uint32_t parity = 0;
+        if constexpr (TcCfg<TEAMS>::kConsumerRegs < TcCfg<TEAMS>::kBaseRegs) tc::setmaxnreg_dec<TcCfg<TEAMS>::kConsumerRegs>();
+        else if constexpr (TcCfg<TEAMS>::kConsumerRegs > TcCfg<TEAMS>::kBaseRegs) tc::setmaxnreg_inc<TcCfg<TEAMS>::kConsumerRegs>();
+        const int g = warp >> 2, qw = warp & 3;
+        const uint32_t d1_col = tmem_base + g * kGroupCols, d2_col = d1_col + kD2Col;
+        const uint32_t lane_sel = (uint32_t)(qw * 32) << 16;
+        const uint32_t w_hi_u = tc::smem_u32(w_hi), w_lo_u = tc::smem_u32(w_lo);
+        const uint32_t stage_u = tc::smem_u32(stage_base);
+        const bool issuer = (qw == 0 && lane == 0);
+        const int seg0 = lane & ~7, d = lane & 7;
+        const int my_tiles = g ? sch.tiles1 : sch.tiles0, my_units = g ? sch.cnt1 : sch.cnt0;
+        uint32_t par_d1 = 0, par_d2 = 0, par_a2 = 0;
 
-        auto issue_l1 = [&](int b, uint32_t a_hi_u, uint32_t a_lo_u) {
-            const TcBlock& B = P.blk[b];
+        // layer 1 of every hidden block of one tile (D1 has a 64-column slot per block); the A stage is free when these MMAs are done
+        auto issue_l1 = [&](int seq) {
+            const int stage = seq % kStages;
+            const uint32_t a_hi_u = stage_u + stage * kStageBytes, a_lo_u = a_hi_u + kTileBytes;
             const uint32_t idesc = tc::make_idesc_bf16(128, 64);
-            const uint32_t w1hi = w_u + b * 4 * kWTileBytes, w1lo = w1hi + kWTileBytes;
-            const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
-            for (int ks = 0; ks < ksn; ++ks) {
-                const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K
-                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, ks > 0);
-                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_hi_u + off), tc::make_sdesc_sw128(w1lo + off), idesc, 1);
-                tc::umma_bf16(d1_col + b * 64, tc::make_sdesc_sw128(a_lo_u + off), tc::make_sdesc_sw128(w1hi + off), idesc, 1);
+            for (int b = 0; b < P.nblocks; ++b) {
+                const TcBlock& B = P.blk[b];
+                const int ks0 = B.k0 >> 4, ksn = B.kcount >> 4;
+                for (int ks = 0; ks < ksn; ++ks) {
+                    const uint32_t off = (uint32_t)(ks0 + ks) * 32;                 // 16 bf16 = 32 bytes along K, same column in A and W1
+                    const uint64_t ah = tc::make_sdesc_sw128(a_hi_u + off), al = tc::make_sdesc_sw128(a_lo_u + off);
+                    const uint64_t wh = tc::make_sdesc_sw128(w_hi_u + B.w1_off + off), wl = tc::make_sdesc_sw128(w_lo_u + B.w1_off + off);
+                    tc::umma_bf16(d1_col + b * 64, ah, wh, idesc, ks > 0);
+                    tc::umma_bf16(d1_col + b * 64, ah, wl, idesc, 1);
+                    tc::umma_bf16(d1_col + b * 64, al, wh, idesc, 1);
+                }
             }
+            tc::umma_commit(&bar_d1[g]);
+            tc::umma_commit(&bar_empty[stage]);
         };
+        // layer 2 of one hidden block: A2 (bf16 hi / lo, packed) is read from TMEM columns [64b + 16ks, +8) / [64b + 16ks + 8, +8)
         auto issue_l2 = [&](int b) {
             const TcBlock& B = P.blk[b];
-            const uint32_t w2hi = w_u + b * 4 * kWTileBytes + 2 * kWTileBytes, w2lo = w2hi + kWTileBytes;
             for (int rr = 0; rr < B.nruns; ++rr) {
                 const TcRun& R = B.runs[rr];
                 const uint32_t idesc = tc::make_idesc_bf16(128, R.n);
-                const uint32_t rowoff = (uint32_t)R.n0 * 128;                    // n0 is a multiple of 16 -> atom aligned
+                const uint32_t rowoff = (uint32_t)(R.n0 - B.w2_row0) * 128;          // multiples of 16 rows: 1024-byte atom aligned
                 for (int ks = 0; ks < 4; ++ks) {
-                    const uint32_t off = (uint32_t)ks * 32;
-                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, (R.accum || ks > 0));
-                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_hi_u + off), tc::make_sdesc_sw128(w2lo + rowoff + off), idesc, 1);
-                    tc::umma_bf16(d2_col + R.n0, tc::make_sdesc_sw128(a2_lo_u + off), tc::make_sdesc_sw128(w2hi + rowoff + off), idesc, 1);
+                    const uint32_t off = B.w2_off + rowoff + (uint32_t)ks * 32;
+                    const uint32_t ahi = d1_col + b * 64 + ks * 16, alo = ahi + 8;
+                    const uint64_t wh = tc::make_sdesc_sw128(w_hi_u + off), wl = tc::make_sdesc_sw128(w_lo_u + off);
+                    tc::umma_bf16_ts(d2_col + R.n0, ahi, wh, idesc, (R.accum || ks > 0));
+                    tc::umma_bf16_ts(d2_col + R.n0, ahi, wl, idesc, 1);
+                    tc::umma_bf16_ts(d2_col + R.n0, alo, wh, idesc, 1);
                 }
             }
         };
 
-        int q = 0;
-        for (int pt = blockIdx.x; pt < num_ptiles; pt += gridDim.x) {
-            const RaySetup r = ray_setup(a, pt, wg);
-            // half 0: semantic logits (19) ; half 1: colour features (32).  acc[32] covers both.
-            float acc[32];
+        bool l1_issued = false;                              // layer 1 of the NEXT tile already in flight (issuer only)
+        int t = 0;
+        for (int ui = 0; ui < my_units; ++ui) {
+            const int unit = blockIdx.x * kGroups + g + ui * unit_stride;
+            const RaySetup r = ray_setup(a, unit, lane >> 3, qw);
+            float acc[kOut - 1];
 #pragma unroll
-            for (int c = 0; c < 32; ++c) acc[c] = 0.f;
-            float acc_w = 0.f, acc_d = 0.f, carry = 1.f;
+            for (int c = 0; c < kOut - 1; ++c) acc[c] = 0.f;
+            float acc_w = 0.f, acc_d = 0.f, T_in = 1.f;
 
-            for (int ch = 0; ch < chunks; ++ch, ++q) {
-                const int stage = q % kTcStages, use = q / kTcStages;
-                const uint32_t a_hi_u = stage_u + stage * 2 * kTileBytes, a_lo_u = a_hi_u + kTileBytes;
-                tc::mbar_wait(&bar_full[stage], use & 1);
-                tc::tc_fence_after();
-                if (a.debug == 2) {                                      // timing experiment: hand the stage straight back
-                    tc::bar_sync(1, kTcConsumerThreads);
-                    if (issuer) tc::mbar_arrive(&bar_empty[stage]);
-                    continue;
+            for (int step = 0; step < a.tiles_per_unit; ++step, ++t) {
+                if (issuer && !l1_issued) {
+                    const int seq = seq_of(sch, g, t);
+                    tc::mbar_wait(&bar_full[seq % kStages], (seq / kStages) & 1);
+                    tc::tc_fence_after();
+                    issue_l1(seq);
                 }
+                l1_issued = false;
+                __syncwarp();
+                tc::mbar_wait(&bar_d1[g], par_d1);
+                par_d1 ^= 1;
+                tc::tc_fence_after();
 
-                // ---- layer 1 of every hidden block in one batch (D1 has a 64-column slot per block); the A stage is free after it
-                if (issuer) {
-                    for (int b = 0; b < P.nblocks; ++b) issue_l1(b, a_hi_u, a_lo_u);
-                    tc::umma_commit(bar_mma);
-                    tc::umma_commit(&bar_empty[stage]);
-                }
-                tc::mbar_wait(bar_mma, parity);
-                parity ^= 1;
-                tc::tc_fence_after();
-                // ---- per block: softplus epilogue in registers -> (wait until layer 2 of the previous block has read A2) -> A2
-                //      -> layer 2 of this block is issued and runs while the next block's softplus is being computed
+                // ---- hidden blocks: softplus epilogue in place, 16 columns at a time, then layer 2 of the block
                 for (int b = 0; b < P.nblocks; ++b) {
-                    uint32_t ph[16], pl[16];
-                    {
-                        float v[32];
-                        tc::tmem_ld32(d1_col + b * 64 + lane_sel + half * 32, v);
-                        const float* bb = b1s + b * 64 + half * 32;
+                    const float* bb = b1s + b * 64;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const float h0 = softplus2(v[2 * j] + bb[2 * j]);
-                            const float h1 = softplus2(v[2 * j + 1] + bb[2 * j + 1]);
+                    for (int c16 = 0; c16 < 4; ++c16) {
+                        const uint32_t col = d1_col + b * 64 + c16 * 16 + lane_sel;
+                        float v[16];
+                        tc::tmem_ld16(col, v);
+                        uint32_t ph[8], pl[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float h0 = softplus2(v[2 * j] + bb[c16 * 16 + 2 * j]);
+                            const float h1 = softplus2(v[2 * j + 1] + bb[c16 * 16 + 2 * j + 1]);
                             const __nv_bfloat162 hh = __floats2bfloat162_rn(h0, h1);
                             const float2 back = __bfloat1622float2(hh);
                             const __nv_bfloat162 ll = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
                             ph[j] = *reinterpret_cast<const uint32_t*>(&hh);
                             pl[j] = *reinterpret_cast<const uint32_t*>(&ll);
                         }
+                        tc::tmem_st8(col, ph);
+                        tc::tmem_st8(col + 8, pl);
                     }
-                    if (b > 0) {                                             // A2 is still being read by layer 2 of block b-1
-                        tc::mbar_wait(bar_mma, parity);
-                        parity ^= 1;
-                    }
-#pragma unroll
-                    for (int c8 = 0; c8 < 4; ++c8) {                       // 8 hidden units = one 16-byte chunk
-                        const uint32_t o = tc::sw128_offset(row, half * 4 + c8);
-                        *reinterpret_cast<uint4*>(a2_hi + o) = make_uint4(ph[c8 * 4], ph[c8 * 4 + 1], ph[c8 * 4 + 2], ph[c8 * 4 + 3]);
-                        *reinterpret_cast<uint4*>(a2_lo + o) = make_uint4(pl[c8 * 4], pl[c8 * 4 + 1], pl[c8 * 4 + 2], pl[c8 * 4 + 3]);
-                    }
-                    tc::fence_async_smem();
+                    tc::tmem_wait_st();
                     tc::tc_fence_before();
-                    tc::bar_sync(1, kTcConsumerThreads);
-                    tc::tc_fence_after();
-                    if (issuer) {
-                        issue_l2(b);
-                        tc::umma_commit(bar_mma);
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&bar_a2[g * kTcMaxBlocks + b]);
+                    if (qw == 0) {
+                        if (lane == 0) {
+                            tc::mbar_wait(&bar_a2[g * kTcMaxBlocks + b], par_a2);
+                            tc::tc_fence_after();
+                            issue_l2(b);
+                            if (b == P.nblocks - 1) {
+                                tc::umma_commit(&bar_d2[g]);
+                                // layer 1 of this group's next tile right behind (MMAs execute in issue order: it overwrites D1 only
+                                // after layer 2 above has read A2 from it) -- if its stage is already full; else after the epilogue
+                                if (t + 1 < my_tiles) {
+                                    const int seq = seq_of(sch, g, t + 1);
+                                    if (tc::mbar_try_wait(&bar_full[seq % kStages], (seq / kStages) & 1)) {
+                                        tc::tc_fence_after();
+                                        issue_l1(seq);
+                                        l1_issued = true;
+                                    }
+                                }
+                            }
+                        }
+                        __syncwarp();
                     }
                 }
-                tc::mbar_wait(bar_mma, parity);
-                parity ^= 1;
+                par_a2 ^= 1;                             // every a2 barrier completes once per tile
+
+                tc::mbar_wait(&bar_d2[g], par_d2);
+                par_d2 ^= 1;
                 tc::tc_fence_after();
 
-                const int s = ch * 32 + lane;
+                // ---- sigma + semantic logits (D2 columns 32..55), compositing weight of this sample
+                const int s = step * kTileDepth + d;
                 const bool live = r.ok && (s < S);
-                float o32[32];
-                if (half == 0) {
-                    // ---- sigma + semantic logits (columns 32..63), compositing weight of this sample
-                    float z0 = 0.f, off0 = 0.f, z1 = 0.f;
-                    if (live) sample_depths(a, r, s, z0, off0, z1);
-                    const float zj = z0 + off0;
-                    tc::tmem_ld32(d2_col + lane_sel + 32, o32);
-                    float sigma = (((P.written >> 3) & 1u) ? o32[19] : 0.f) + b2s[51];
+                float z0 = 0.f, off0 = 0.f, z1 = 0.f;
+                if (live) sample_depths(a, r, s, z0, off0, z1);
+                const float zj = z0 + off0;
+                float w;
+                {
+                    float o16[16], o8[8];
+                    tc::tmem_ld16(d2_col + lane_sel + 32, o16);
+                    tc::tmem_ld8(d2_col + lane_sel + 48, o8);
+                    float sigma = (((P.written >> 3) & 1u) ? o8[3] : 0.f) + b2s[51];
                     if (a.noise != nullptr && live) sigma += a.noise_std * a.noise[r.sample_base + s];
                     const float delta = (s + 1 < S) ? (z1 - zj) * r.dnorm : 1e10f;
                     const float dens = (a.clamp_mode == IDE3D_CLAMP_SOFTPLUS) ? softplus_precise(sigma) : fmaxf(sigma, 0.f);
                     const float alpha = live ? 1.f - expf(-delta * dens) : 0.f;
                     const float keep = live ? (1.f - alpha + 1e-10f) : 1.f;
-                    float total;
-                    const float T = warp_exclusive_product(keep, lane, total) * carry;
-                    carry *= total;
-                    float w = alpha * T;
-                    acc_w += w;
-                    if (a.last_back && ch == chunks - 1) {
-                        const float wsum_all = warp_sum(acc_w);
-                        if (s == S - 1) w += 1.f - wsum_all;
+                    // exclusive product over the 8 samples of the ray in sample order, times the transmittance carried in
+                    float tr = T_in, mine = T_in;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float kj = __shfl_sync(kFull, keep, seg0 + j);
+                        if (j == d) mine = tr;
+                        tr *= kj;
                     }
-                    wbuf[row] = w;                                           // hand the weight to the colour warp
-                    tc::bar_sync(2 + wg, 64);
+                    T_in = tr;
+                    w = alpha * mine;
+                    acc_w += w;
+                    if (a.last_back && step == a.tiles_per_unit - 1) {
+                        float ws = acc_w;
+                        ws += __shfl_xor_sync(kFull, ws, 1); ws += __shfl_xor_sync(kFull, ws, 2); ws += __shfl_xor_sync(kFull, ws, 4);
+                        if (s == S - 1) w += 1.f - ws;
+                    }
                     if (a.out_weights != nullptr && live) a.out_weights[r.sample_base + s] = w;
                     acc_d = fmaf(w, zj, acc_d);
 #pragma unroll
-                    for (int c = 0; c < 19; ++c) {
-                        const float v = (((P.written >> (2 + (c >> 4))) & 1u) ? o32[c] : 0.f) + b2s[32 + c];
-                        acc[c] = fmaf(w, v, acc[c]);
-                    }
-                } else {
-                    // ---- colour features (columns 0..31)
-                    tc::tmem_ld32(d2_col + lane_sel, o32);
-                    tc::bar_sync(2 + wg, 64);
-                    const float w = wbuf[row];
+                    for (int c = 0; c < 16; ++c) acc[32 + c] = fmaf(w, (((P.written >> 2) & 1u) ? o16[c] : 0.f) + b2s[32 + c], acc[32 + c]);
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float v = (((P.written >> (c >> 4)) & 1u) ? o32[c] : 0.f) + b2s[c];
-                        acc[c] = fmaf(w, v, acc[c]);
-                    }
+                    for (int c = 0; c < 3; ++c) acc[48 + c] = fmaf(w, (((P.written >> 3) & 1u) ? o8[c] : 0.f) + b2s[48 + c], acc[48 + c]);
                 }
-                tc::tc_fence_before();
-                tc::bar_sync(1, kTcConsumerThreads);      // D2 drained and wbuf consumed before the next tile reuses them
+                // ---- colour features (D2 columns 0..31)
+#pragma unroll
+                for (int c16 = 0; c16 < 2; ++c16) {
+                    float o16[16];
+                    tc::tmem_ld16(d2_col + lane_sel + c16 * 16, o16);
+#pragma unroll
+                    for (int c = 0; c < 16; ++c)
+                        acc[c16 * 16 + c] = fmaf(w, (((P.written >> c16) & 1u) ? o16[c] : 0.f) + b2s[c16 * 16 + c], acc[c16 * 16 + c]);
+                }
+                tc::tc_fence_before();                   // D2 reads ordered before the a2 arrival that lets layer 2 of the next tile overwrite it
             }
 
-            // ---- per-ray reduction and store
+            // ---- per-ray reduction over the 8 depth lanes and store (weights_sum is the sum BEFORE the last_back correction,
+            //      volumetric_rendering.py:56-72)
+            float wsum = acc_w, depth = acc_d;
+#pragma unroll
+            for (int m = 1; m < 8; m <<= 1) { wsum += __shfl_xor_sync(kFull, wsum, m); depth += __shfl_xor_sync(kFull, depth, m); }
+            if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
             const long long ray_index = (long long)r.n * (a.res_w * a.res_h) + r.ray;
             float* of = a.out_feat + ray_index * (kOut - 1);
-            if (half == 0) {
-                const float wsum = warp_sum(acc_w);
-                if (lane == 0) wsumbuf[wg] = wsum;
-                tc::bar_sync(2 + wg, 64);
-                float depth = warp_sum(acc_d);
-                float mine = 0.f;
 #pragma unroll
-                for (int c = 0; c < 19; ++c) {
-                    const float v = warp_sum(acc[c]);
-                    if (c == lane) mine = v;
-                }
-                if (a.white_back) mine += 1.f - wsum;
-                if (a.max_depth != 0.f) depth += (1.f - wsum) * a.max_depth;
-                if (a.fill_weight) mine = wsum;
-                if (r.ok) {
-                    if (lane < 19) of[32 + lane] = mine;
-                    if (lane == 0) a.out_depth[ray_index] = depth;
-                }
-            } else {
-                tc::bar_sync(2 + wg, 64);
-                const float wsum = wsumbuf[wg];
-                float mine = 0.f;
-#pragma unroll
-                for (int c = 0; c < 32; ++c) {
-                    const float v = warp_sum(acc[c]);
-                    if (c == lane) mine = v;
-                }
-                if (a.white_back) mine += 1.f - wsum;
-                if (a.fill_weight) mine = wsum;
-                if (r.ok) of[lane] = mine;
+            for (int c = 0; c < kOut - 1; ++c) {
+                float v = acc[c];
+                v += __shfl_xor_sync(kFull, v, 1); v += __shfl_xor_sync(kFull, v, 2); v += __shfl_xor_sync(kFull, v, 4);
+                if (a.white_back) v += 1.f - wsum;
+                if (a.fill_weight) v = wsum;
+                if (r.ok && (c & 7) == d) of[c] = v;
             }
-            tc::bar_sync(1, kTcConsumerThreads);          // wsumbuf is reused by the next pixel tile
+            if (r.ok && d == 0) a.out_depth[ray_index] = depth;
         }
     }
 
     tc::tc_fence_before();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 0) tc::tmem_dealloc(tmem_base, kGroups * kGroupCols);
 }
 
-// Build the hidden-block program from the head list.  Returns false when the decoder does not fit
-// (hidden not a multiple of 64, more than kTcMaxBlocks blocks, outputs beyond 64 columns).
+// Build the hidden-block program from the head list and lay the weight tiles out compactly.  Returns false when the decoder does
+// not fit (hidden not a multiple of 64, more than kTcMaxBlocks blocks, outputs beyond 64 columns).
 static bool build_program(const ide3d_decoder& d, TcProgram& P) {
     P.nblocks = 0;
     P.written = 0;
@@ -468,6 +594,7 @@ static bool build_program(const ide3d_decoder& d, TcProgram& P) {
             B.out0 = H.out_offset; B.outc = H.out_count;
             // layer-2 column range in units of 16, split into runs of equal "already written" status
             const int g0 = H.out_offset / 16, g1 = (H.out_offset + H.out_count + 15) / 16;
+            B.w2_row0 = g0 * 16;
             B.nruns = 0;
             int gi = g0;
             while (gi < g1) {
@@ -480,7 +607,37 @@ static bool build_program(const ide3d_decoder& d, TcProgram& P) {
             for (int q = g0; q < g1; ++q) P.written |= 1u << q;
         }
     }
-    return P.nblocks > 0;
+    if (P.nblocks == 0) return false;
+    // weight layout inside one part (hi or lo): W1 tiles of 8 KB ([64 hidden x 64 inputs]; two 32-input blocks with different k0
+    // share a tile), then the W2 row blocks ((g1 - g0) * 16 rows x 128 bytes)
+    int ntiles = 0, half_free[kTcMaxBlocks];          // half_free[t]: k0 of the half still free in tile t, or -1
+    for (int b = 0; b < P.nblocks; ++b) {
+        TcBlock& B = P.blk[b];
+        int tile = -1;
+        if (B.kcount == 32)
+            for (int t = 0; t < ntiles; ++t) if (half_free[t] == B.k0) { tile = t; half_free[t] = -1; break; }
+        if (tile < 0) {
+            tile = ntiles++;
+            half_free[tile] = (B.kcount == 32) ? (32 - B.k0) : -1;
+        }
+        B.w1_off = tile * 64 * 128;
+    }
+    int off = ntiles * 64 * 128;
+    for (int b = 0; b < P.nblocks; ++b) {
+        TcBlock& B = P.blk[b];
+        const int rows = ((B.out0 + B.outc + 15) / 16) * 16 - B.w2_row0;
+        B.w2_off = off;
+        off += rows * 128;
+    }
+    P.wpart = (off + 1023) & ~1023;
+    return true;
+}
+
+static int env_int(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    if (!v) return dflt;
+    const int x = atoi(v);
+    return (x < lo || x > hi) ? dflt : x;
 }
 
 // entry used by ide3d_raymarch_fwd (raymarch.cu); IDE3D_UNSUPPORTED when this decoder / layout has no TC kernel
@@ -488,6 +645,8 @@ int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaS
     if (!channels_last) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: planes must be channels-last");
     if (p->tex.stride_h != p->seg.stride_h || p->tex.stride_w != p->seg.stride_w)
         IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: tex and seg planes must share strides");
+    if (((long long)p->tex.h * p->tex.stride_h + (long long)p->tex.w * p->tex.stride_w + 96) * 4 >= (1ll << 31))
+        IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: plane too large for 32-bit byte offsets");
     TcArgs a;
     if (!build_program(p->dec, a.prog)) IDE3D_FAIL(IDE3D_UNSUPPORTED, "raymarch_tc: decoder shape not supported");
     a.tex = make_view(p->tex); a.seg = make_view(p->seg); a.dec = p->dec;
@@ -501,14 +660,22 @@ int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaS
     a.fill_weight = p->fill_weight; a.max_depth = p->max_depth;
     a.noise_std = p->noise_std; a.noise = (p->noise_std != 0.f) ? p->noise : nullptr;
     a.out_feat = p->out_feat; a.out_depth = p->out_depth; a.out_weights = p->out_weights;
-    a.tiles_x = ceil_div(p->res_w, 2); a.tiles_y = ceil_div(p->res_h, 2);
-    const char* dbg = getenv("IDE3D_TC_DEBUG");
-    a.debug = dbg ? atoi(dbg) : 0;
-    IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    const int num_tiles = a.tiles_x * a.tiles_y * a.n;
+    a.units_x = ceil_div(p->res_w, kUnitW); a.units_y = ceil_div(p->res_h, kUnitH);
+    a.num_units = a.units_x * a.units_y * a.n;
+    a.tiles_per_unit = ceil_div(p->num_steps, kTileDepth);
+    // tuning knob: gather instruction shape
+    a.ray_major = env_int("IDE3D_TC_RAY_MAJOR", 1, 0, 1);
+    const int teams = env_int("IDE3D_TC_TEAMS", 3, 2, kMaxTeams);
+    const int smem = 2 * a.prog.wpart + teams * kStageBytes + (kTcMaxBlocks * 64 + 64) * 4 + (2 * kMaxTeams + (2 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
     int grid = sm_count();
-    if (grid > num_tiles) grid = num_tiles;
-    raymarch_tc_kernel<<<grid, kTcThreads, kTcSmemBytes, st>>>(a);
+    if (grid * kGroups > a.num_units) grid = ceil_div(a.num_units, kGroups);
+    if (teams == 2) {
+        IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        raymarch_tc_kernel<2><<<grid, TcCfg<2>::kThreads, smem, st>>>(a);
+    } else {
+        IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        raymarch_tc_kernel<3><<<grid, TcCfg<3>::kThreads, smem, st>>>(a);
+    }
     IDE3D_CHECK_LAUNCH("raymarch_tc_kernel");
     return IDE3D_OK;
 }

@@ -29,12 +29,14 @@ import torch
 pytestmark = pytest.mark.gpu
 
 # relative tolerances (x max|ref|): (fp32 convolutions, TF32 convolutions)
+# measured on B200 (profiles/r02a_parity_fullsize_and_determinism.txt): fp32 planes 2.6e-6, feat 6.3e-6, depth 9.1e-7, weights 3.6e-6,
+# image 1.1e-5, uint8 <= 1 level;  TF32 (the benched arithmetic) planes 8.6e-4, image 2.1e-3, uint8 <= 2 levels (mean 0.08)
 TOL = {
-    'planes': (2e-4, 2e-2),
-    'feat': (2e-4, 2e-4),        # renderer on identical planes: independent of the convolution precision
-    'depth': (2e-5, 2e-5),
-    'weights': (1e-4, 1e-4),
-    'image': (5e-4, 5e-2),
+    'planes': (3e-5, 5e-3),
+    'feat': (1e-4, 1e-4),        # renderer on identical planes: independent of the convolution precision
+    'depth': (1e-5, 1e-5),
+    'weights': (5e-5, 5e-5),
+    'image': (1e-4, 1e-2),
 }
 
 
@@ -105,7 +107,7 @@ def test_fullsize_synthesis_matches_cpu_oracle(fullsize, tf32):
     print('full-size parity', 'tf32' if tf32 else 'fp32', rep)
     for k, tol in TOL.items():
         assert rep[k] <= tol[col], (k, rep, tol[col])
-    assert rep['uint8_max_levels'] <= (1 if not tf32 else 24), rep
+    assert rep['uint8_max_levels'] <= (1 if not tf32 else 6), rep
 
 
 def test_sigma_grid_256_is_bit_identical_to_create_samples_path(fullsize):

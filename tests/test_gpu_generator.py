@@ -112,4 +112,7 @@ def test_stream_frames_matches_batch_loop_and_lands_in_pinned_host_memory(case):
         G.cpu()
     assert streamed.dtype == torch.uint8 and streamed.device.type == 'cpu' and streamed.is_pinned() and tuple(streamed.shape) == (4, 3, 128, 128)
     assert (streamed.int() - looped.cpu().int()).abs().max() <= 1            # batch 2 vs batch 4: cuDNN may pick different algorithms
-    assert (streamed[:2].int() - streamed[2:].int()).abs().max() <= 1        # the two halves are the same inputs (two batches)
+    # the two halves are the same inputs rendered as two batches of the same size: bit-identical (scripts/determinism.py on B200,
+    # profiles/r02a_parity_fullsize_and_determinism.txt: every stage is run-to-run bit-equal under all cudnn.benchmark /
+    # cudnn.deterministic settings; the one-level difference seen in round 1 came from comparing DIFFERENT batch sizes, above)
+    assert torch.equal(streamed[:2], streamed[2:])
