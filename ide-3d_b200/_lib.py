@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, 'lib', 'libide3d_b200.so')
 
 OK, UNSUPPORTED, INVALID, CUDA_ERROR = 0, -1, -2, -3
 F32, F16, F64 = 0, 1, 2
-JITTER_NONE, JITTER_TENSOR, JITTER_HASH = 0, 1, 2
+JITTER_NONE, JITTER_TENSOR, JITTER_HASH, JITTER_ZVALS = 0, 1, 2, 3
 CLAMP_SOFTPLUS, CLAMP_RELU = 0, 1
 PRECISION = {'auto': 0, 'fp32': 1, 'tc': 2}
 

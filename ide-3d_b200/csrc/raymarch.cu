@@ -94,6 +94,9 @@ __global__ void __launch_bounds__(kBlock, 1) raymarch_kernel(const RayArgs a) {
                     const uint32_t gi = (uint32_t)(sample_base + s);
                     off0 = (jitter_hash(gi, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
                     if (s + 1 < S) z1 += (jitter_hash(gi + 1u, a.seed_lo, a.seed_hi) - 0.5f) * spacing;
+                } else if (a.jitter_mode == IDE3D_JITTER_ZVALS) {          // depths given per sample (hierarchical second pass)
+                    z0 = a.jitter_u[sample_base + s];
+                    z1 = (s + 1 < S) ? a.jitter_u[sample_base + s + 1] : 0.f;
                 }
             }
             const float zj = z0 + off0;
@@ -220,8 +223,8 @@ extern "C" int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t
     IDE3D_REQUIRE(p->cam2world && p->out_feat && p->out_depth, "raymarch: null camera/output");
     IDE3D_REQUIRE(p->clamp_mode == IDE3D_CLAMP_SOFTPLUS || p->clamp_mode == IDE3D_CLAMP_RELU,
                   "Need to choose clamp mode");   // volumetric_rendering.py:51-52
-    IDE3D_REQUIRE(p->jitter_mode >= 0 && p->jitter_mode <= 2, "raymarch: bad jitter mode");
-    IDE3D_REQUIRE(p->jitter_mode != IDE3D_JITTER_TENSOR || p->jitter_u, "raymarch: jitter tensor missing");
+    IDE3D_REQUIRE(p->jitter_mode >= 0 && p->jitter_mode <= 3, "raymarch: bad jitter mode");
+    IDE3D_REQUIRE((p->jitter_mode != IDE3D_JITTER_TENSOR && p->jitter_mode != IDE3D_JITTER_ZVALS) || p->jitter_u, "raymarch: jitter / depth tensor missing");
     IDE3D_REQUIRE((long long)p->n * p->res_w * p->res_h * p->num_steps < (1ll << 32),
                   "raymarch: more than 2^32 samples per call");
     IDE3D_REQUIRE(p->precision >= IDE3D_PRECISION_AUTO && p->precision <= IDE3D_PRECISION_TC, "raymarch: bad precision");

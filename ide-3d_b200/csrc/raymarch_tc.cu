@@ -155,6 +155,9 @@ __device__ __forceinline__ void sample_depths(const TcArgs& a, const RaySetup& r
         const uint32_t gi = (uint32_t)(r.sample_base + s);
         off0 = (jitter_hash(gi, a.seed_lo, a.seed_hi) - 0.5f) * r.spacing;
         if (s + 1 < S) z1 += (jitter_hash(gi + 1u, a.seed_lo, a.seed_hi) - 0.5f) * r.spacing;
+    } else if (a.jitter_mode == IDE3D_JITTER_ZVALS) {                  // depths given per sample (hierarchical second pass)
+        z0 = a.jitter_u[r.sample_base + s];
+        z1 = (s + 1 < S) ? a.jitter_u[r.sample_base + s + 1] : 0.f;
     }
 }
 

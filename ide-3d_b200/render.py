@@ -64,15 +64,23 @@ def _decoder(dec, device):
 def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, fov=18.0, ray_start=2.25,
              ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
              clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None,
-             return_weights=False, convert_layout=True, precision='auto'):
+             return_weights=False, convert_layout=True, precision='auto', z_vals=None):
     """Fused render of N frames.  -> feat [N,R,51], depth [N,R,1], weights [N,R,S,1] | None.
     jitter_u: explicit uniforms [N,R,S]; jitter_seed: in-kernel counter hash; neither: no jitter.
+    z_vals: explicit sample depths [N,R,S] ascending along S (replaces linspace + jitter; num_steps is taken from it).
     precision: 'auto' | 'fp32' (CUDA-core FFMA decoder) | 'tc' (tcgen05 decoder, bf16x3 products).
     Differentiable w.r.t. the planes, the camera and the decoder parameters (when `decoder` is a list of heads holding the
     live parameters): the forward is the same fused kernel, the backward is render_grad.RaymarchFunction."""
     kw = dict(resolution=resolution, num_steps=num_steps, fov=fov, ray_start=ray_start, ray_end=ray_end, box_scale=box_scale,
               jitter_seed=jitter_seed, noise_std=noise_std, clamp_mode=clamp_mode, last_back=last_back, white_back=white_back,
               max_depth=max_depth, fill_mode=fill_mode, return_weights=return_weights, convert_layout=convert_layout, precision=precision)
+    if z_vals is not None:
+        if torch.is_grad_enabled() and z_vals.requires_grad:
+            raise RuntimeError('ide3d_b200.render.raymarch: z_vals is not differentiable (the reference detaches the importance samples too)')
+        kw.update(z_vals=z_vals, num_steps=int(z_vals.shape[-1]))
+        num_steps = int(z_vals.shape[-1])
+        if torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in [planes_tex, planes_seg, cam2world]):
+            raise NotImplementedError('ide3d_b200.render.raymarch: the backward pass has no explicit-depth (hierarchical) mode yet')
     if isinstance(decoder, PackedDecoder):
         meta, params = decoder.meta, list(decoder.tensors)
     else:
@@ -97,10 +105,69 @@ def raymarch(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), nu
     return _raymarch_impl(planes_tex, planes_seg, decoder, cam2world, jitter_u=jitter_u, noise=noise, **kw)
 
 
+def coarse_depths(n, resolution, num_steps, ray_start=2.25, ray_end=3.3, jitter_u=None, jitter_seed=None, device='cuda'):
+    """z_vals [N, R, S] of the first (stratified) pass exactly as the fused kernel generates them: torch.linspace(ray_start, ray_end, S)
+    (volumetric_rendering.py:91) + (u - 0.5) * (z[1] - z[0]) (:99-105), u = jitter_u or the kernel's counter hash."""
+    W, H = (resolution, resolution) if isinstance(resolution, int) else resolution
+    R, S = W * H, int(num_steps)
+    z = torch.linspace(ray_start, ray_end, S, device=device, dtype=torch.float32)
+    zv = z.reshape(1, 1, S).expand(n, R, S)
+    if jitter_u is None and jitter_seed is not None:
+        from .render_grad import hash_uniform
+        jitter_u = hash_uniform(n * R * S, jitter_seed, device)
+    if jitter_u is None:
+        return zv.contiguous()
+    spacing = (z[1] - z[0]) if S > 1 else z.new_zeros(())
+    return zv + (jitter_u.to(device=device, dtype=torch.float32).reshape(n, R, S) - 0.5) * spacing
+
+
+@torch.no_grad()
+def raymarch_hierarchical(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, n_importance=None,
+                          ray_start=2.25, ray_end=3.3, jitter_u=None, jitter_seed=None, importance_u=None, det=False,
+                          return_weights=False, return_depths=False, **kw):
+    """Two-pass (coarse -> importance) render, the hierarchical sampling that `sample_pdf` exists for
+    (volumetric_rendering.py:224-265; used as in pi-GAN / StyleNeRF's renderers, dnnlib/camera.py:638):
+        1. coarse fused pass over the stratified depths, returning the compositing weights;
+        2. `ide3d_sample_pdf`: n_importance depths per ray drawn from the piecewise-constant pdf weights[1:-1] (+1e-5) over the
+           midpoints of the coarse depths (importance_u [N*R, n_importance] injects the uniform draws; det=True uses linspace);
+        3. the coarse and fine depths merged and sorted per ray; second fused pass over all S + n_importance samples with the depths
+           read from that tensor (IDE3D_JITTER_ZVALS) -- compositing over the merged set, as the reference composition does.
+    Forward only.  -> feat [N,R,51], depth [N,R,1], weights [N,R,S+n_importance,1] | None (, z_vals [N,R,S+n_importance])."""
+    from .training.volumetric_rendering import sample_pdf_u
+    L.require_cuda(planes_tex, planes_seg, cam2world)
+    dev = planes_tex.device
+    n = planes_tex.shape[0]
+    W, H = (resolution, resolution) if isinstance(resolution, int) else resolution
+    R, S = W * H, int(num_steps)
+    n_imp = S if n_importance is None else int(n_importance)
+    assert S >= 3, 'hierarchical sampling needs at least 3 coarse samples (weights[1:-1])'
+    tex, seg = as_planes(planes_tex), as_planes(planes_seg)
+    dec = _decoder(decoder, dev)
+    z = coarse_depths(n, (W, H), S, ray_start, ray_end, jitter_u=jitter_u, jitter_seed=jitter_seed, device=dev)
+    kw = dict(kw, convert_layout=False)
+    noise_std = float(kw.pop('noise_std', 0.0) or 0.0)
+    kw.pop('noise', None)                                  # drawn per pass (the two passes have different sample counts)
+    draw = (lambda s_: dict(noise=torch.randn(n, R, s_, device=dev), noise_std=noise_std)) if noise_std else (lambda s_: {})
+    _, _, w = _raymarch_impl(tex, seg, dec, cam2world, resolution=(W, H), ray_start=ray_start, ray_end=ray_end, z_vals=z,
+                             num_steps=S, return_weights=True, **draw(S), **kw)
+    z_mid = 0.5 * (z[..., :-1] + z[..., 1:])
+    if det:
+        u = torch.linspace(0, 1, n_imp, device=dev).expand(n * R, n_imp)
+    elif importance_u is not None:
+        u = importance_u.to(device=dev, dtype=torch.float32).reshape(n * R, n_imp)
+    else:
+        u = torch.rand(n * R, n_imp, device=dev)
+    fine = sample_pdf_u(z_mid.reshape(n * R, S - 1), w.reshape(n * R, S)[:, 1:-1] + 1e-5, u)
+    all_z = torch.sort(torch.cat([z, fine.reshape(n, R, n_imp)], -1), dim=-1).values
+    feat, depth, weights = _raymarch_impl(tex, seg, dec, cam2world, resolution=(W, H), ray_start=ray_start, ray_end=ray_end,
+                                          z_vals=all_z, num_steps=S + n_imp, return_weights=return_weights, **draw(S + n_imp), **kw)
+    return (feat, depth, weights, all_z) if return_depths else (feat, depth, weights)
+
+
 def _raymarch_impl(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 64), num_steps=48, fov=18.0, ray_start=2.25,
                    ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
                    clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None,
-                   return_weights=False, convert_layout=True, precision='auto'):
+                   return_weights=False, convert_layout=True, precision='auto', z_vals=None):
     if clamp_mode not in ('softplus', 'relu'):
         raise ValueError('Need to choose clamp mode')
     if fill_mode not in (None, 'weight'):
@@ -122,7 +189,10 @@ def _raymarch_impl(planes_tex, planes_seg, decoder, cam2world, resolution=(64, 6
     p.cam2world = L.ptr(cam)
     p.n, p.res_w, p.res_h, p.num_steps = n, W, H, S
     p.fov_deg, p.ray_start, p.ray_end, p.box_scale = float(fov), float(ray_start), float(ray_end), float(box_scale)
-    if jitter_u is not None:
+    if z_vals is not None:
+        z_vals = z_vals.detach().to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous()
+        p.jitter_mode, p.jitter_u = L.JITTER_ZVALS, L.ptr(z_vals)
+    elif jitter_u is not None:
         jitter_u = jitter_u.to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous()
         p.jitter_mode, p.jitter_u = L.JITTER_TENSOR, L.ptr(jitter_u)
     elif jitter_seed is not None:

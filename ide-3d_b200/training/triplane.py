@@ -97,8 +97,12 @@ class TriPlaneRenderer(torch.nn.Module):
 
     def forward(self, img_v, seg_v, cam2world, img_size=64, num_steps=48, fov=18.0, ray_start=2.25, ray_end=3.3,
                 nerf_noise=0.0, perturb='hash', jitter_u=None, seed=None, clamp_mode='softplus', last_back=False,
-                white_back=False, max_depth=None, fill_mode=None, return_weights=False):
+                white_back=False, max_depth=None, fill_mode=None, return_weights=False, hierarchical=False, n_importance=None,
+                importance_u=None):
         """-> feat [N, R, 51] (32 colour + 19 semantic), depth [N, R, 1], weights [N, R, S, 1] | None.
+        hierarchical: two-pass importance sampling (render.raymarch_hierarchical; sample_pdf, volumetric_rendering.py:224-265) with
+        n_importance (default num_steps) extra samples per ray; forward only.  Off by default: whether the released generator samples
+        hierarchically is not recoverable from the reference tree.
         perturb: 'hash' (in-kernel counter hash seeded from torch's CPU generator), 'rand' (torch.rand on the device,
         the draw the reference makes at volumetric_rendering.py:101), or None/False (no jitter)."""
         n = img_v.shape[0]
@@ -112,6 +116,15 @@ class TriPlaneRenderer(torch.nn.Module):
         noise = torch.randn([n, res[0] * res[1], num_steps], device=img_v.device) if nerf_noise else None
         # live parameters (differentiable) when a gradient can reach them, else the cached device copy
         train = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
+        if hierarchical:
+            if train or (torch.is_grad_enabled() and (img_v.requires_grad or seg_v.requires_grad or cam2world.requires_grad)):
+                raise NotImplementedError('TriPlaneRenderer: hierarchical sampling is forward-only (run under torch.no_grad())')
+            return render.raymarch_hierarchical(img_v, seg_v, self.packed(), cam2world, resolution=res, num_steps=num_steps,
+                                                n_importance=n_importance, fov=fov, ray_start=ray_start, ray_end=ray_end,
+                                                box_scale=self.box_scale, jitter_u=jitter_u, jitter_seed=seed, importance_u=importance_u,
+                                                det=perturb in (None, False, 'none'), noise_std=float(nerf_noise or 0.0),
+                                                clamp_mode=clamp_mode, last_back=last_back, white_back=white_back, max_depth=max_depth,
+                                                fill_mode=fill_mode, return_weights=return_weights)
         return render.raymarch(img_v, seg_v, self.heads() if train else self.packed(), cam2world, resolution=res, num_steps=num_steps, fov=fov,
                                ray_start=ray_start, ray_end=ray_end, box_scale=self.box_scale, jitter_u=jitter_u,
                                jitter_seed=seed, noise=noise, noise_std=float(nerf_noise or 0.0), clamp_mode=clamp_mode,
@@ -201,7 +214,7 @@ class SynthesisNetwork(torch.nn.Module):
         kw = dict(self.rendering_kwargs)
         kw.update({k: v for k, v in (render_params or {}).items() if k in ('fov', 'num_steps', 'ray_start', 'ray_end',
                                                                           'nerf_noise', 'white_back', 'last_back',
-                                                                          'clamp_mode', 'perturb')})
+                                                                          'clamp_mode', 'perturb', 'hierarchical', 'n_importance')})
         kw.update(render_overrides)
         n = ws.shape[0]
         if c is not None:

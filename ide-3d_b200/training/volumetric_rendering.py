@@ -202,22 +202,29 @@ def create_world2cam_matrix(forward_vector, origin, device=None):
 
 
 # ----------------------------------------------------------------------------------------------- importance pdf
+def sample_pdf_u(bins, weights, u, eps=1e-5):
+    """sample_pdf with the uniform draws u [R, N_importance] given (ide3d_sample_pdf: cumsum, searchsorted, gather, lerp in one kernel)."""
+    _cuda_only(bins, weights, u)
+    n_rays, n_s = weights.shape
+    n_imp = u.shape[1]
+    b, w, u = _f32(bins), _f32(weights), _f32(u)
+    out = torch.empty([n_rays, n_imp], device=b.device, dtype=torch.float32)
+    with torch.cuda.device(b.device):
+        rc = L.get_lib().ide3d_sample_pdf(L.ptr(b), L.ptr(w), L.ptr(u), n_rays, n_s, n_imp, float(eps), L.ptr(out), L.stream_ptr(b.device))
+    L.check(rc)
+    return out
+
+
 def sample_pdf(bins, weights, N_importance, det=False, eps=1e-5):
     """Inverse-CDF importance sampling: bins [R, S+1], weights [R, S] -> samples [R, N_importance]."""
     _cuda_only(bins, weights)
     L.forbid_grad('sample_pdf', bins, weights)
-    n_rays, n_s = weights.shape
+    n_rays = weights.shape[0]
     if det:
         u = torch.linspace(0, 1, N_importance, device=bins.device).expand(n_rays, N_importance)
     else:
         u = torch.rand(n_rays, N_importance, device=bins.device)
-    u = u.contiguous()
-    b, w = _f32(bins), _f32(weights)
-    out = torch.empty([n_rays, N_importance], device=b.device, dtype=torch.float32)
-    rc = L.get_lib().ide3d_sample_pdf(L.ptr(b), L.ptr(w), L.ptr(u), n_rays, n_s, N_importance, float(eps), L.ptr(out),
-                                      L.stream_ptr(b.device))
-    L.check(rc)
-    return out
+    return sample_pdf_u(bins, weights, u.contiguous(), eps)
 
 
 class LookAtPoseSampler:

@@ -207,7 +207,9 @@ typedef struct ide3d_decoder {
     ide3d_mlp_head heads[4];
 } ide3d_decoder;
 
-enum ide3d_jitter { IDE3D_JITTER_NONE = 0, IDE3D_JITTER_TENSOR = 1, IDE3D_JITTER_HASH = 2 };
+/* ZVALS: jitter_u holds the depth of every sample itself, [N, R, S] ascending along S (the merged coarse + importance samples of
+ * a hierarchical second pass, volumetric_rendering.py:224-265): point = ray direction * z, no linspace, no jitter. */
+enum ide3d_jitter { IDE3D_JITTER_NONE = 0, IDE3D_JITTER_TENSOR = 1, IDE3D_JITTER_HASH = 2, IDE3D_JITTER_ZVALS = 3 };
 enum ide3d_clamp { IDE3D_CLAMP_SOFTPLUS = 0, IDE3D_CLAMP_RELU = 1 };
 /* AUTO: tensor cores when the decoder / layout allows, else CUDA cores.  FP32: CUDA-core FFMA, plain fp32.
  * TC: tcgen05 tensor cores, every product as bf16 hi*hi + hi*lo + lo*hi with fp32 accumulation (16-bit operand
@@ -224,7 +226,7 @@ typedef struct ide3d_raymarch_params {
     float fov_deg, ray_start, ray_end;
     float box_scale;            /* world -> plane grid units (2 / box_warp) */
     int jitter_mode;            /* ide3d_jitter */
-    const float* jitter_u;      /* [N, R, S] uniforms in [0,1) when jitter_mode == TENSOR */
+    const float* jitter_u;      /* [N, R, S] uniforms in [0,1) when jitter_mode == TENSOR; sample depths when ZVALS */
     uint64_t jitter_seed;       /* when jitter_mode == HASH */
     int clamp_mode;             /* ide3d_clamp */
     int last_back, white_back;

@@ -283,6 +283,41 @@ def render_frames(planes_tex, planes_seg, decoder, cam2world, fov=18.0, num_step
     return rgb, depth, weights
 
 
+def render_frames_hierarchical(planes_tex, planes_seg, decoder, cam2world, fov=18.0, num_steps=48, n_importance=None,
+                               ray_start=2.25, ray_end=3.3, resolution=(64, 64), box_scale=2.0, jitter_u=None,
+                               jitter_seed=None, importance_u=None, det=False, clamp_mode='softplus', last_back=False,
+                               white_back=False, max_depth=None):
+    """Two-pass render around the reference's own sample_pdf (volumetric_rendering.py:224-265).  The reference tree holds the
+    function but no caller (the generator class is absent), so the COMPOSITION is the one the function's
+    docstring prescribes (bins = midpoints of the coarse depths, weights = coarse weights[1:-1]; nerf_pl / pi-GAN order):
+    coarse chain -> weights (+1e-5) -> sample_pdf -> fine points = origin + direction * z -> decode -> merge by sorted depth
+    -> composite over all samples.  Parity of the composition is therefore unpinned; every stage in it is a pinned one.
+    importance_u [N*HW, n_importance] injects the uniform draws of sample_pdf (det=True: linspace)."""
+    N = planes_tex.shape[0]
+    W, H = resolution
+    S = num_steps
+    n_imp = S if n_importance is None else n_importance
+    st = render_frames(planes_tex, planes_seg, decoder, cam2world, fov=fov, num_steps=S, ray_start=ray_start, ray_end=ray_end,
+                       resolution=resolution, box_scale=box_scale, jitter_u=jitter_u, jitter_seed=jitter_seed,
+                       clamp_mode=clamp_mode, return_stages=True)
+    zv, w = st['z_vals'], st['weights']                                   # [N,HW,S,1]
+    _, _, d = initial_rays(N, S, fov, resolution, ray_start, ray_end)
+    _, dw, ow = to_world(torch.zeros(N, W * H, 1, 3), d, cam2world.float())
+    z = zv.reshape(N * W * H, S)
+    z_mid = 0.5 * (z[:, :-1] + z[:, 1:])
+    fine = sample_pdf(z_mid, w.reshape(N * W * H, S)[:, 1:-1] + 1e-5, n_imp, det=det, u=importance_u).reshape(N, W * H, n_imp, 1)
+    fine_pts = ow.unsqueeze(2) + dw.unsqueeze(2) * fine
+    coords = fine_pts.reshape(N, -1, 3) * box_scale
+    out_f = decoder(sample_triplane(coords, planes_tex), sample_triplane(coords, planes_seg)).reshape(N, W * H, n_imp, N_OUT)
+    all_z = torch.cat([zv, fine], -2)
+    all_out = torch.cat([st['raw'], out_f], -2)
+    all_z, idx = torch.sort(all_z, dim=-2)
+    all_out = torch.gather(all_out, -2, idx.expand(-1, -1, -1, N_OUT))
+    rgb, depth, weights = composite(all_out, d, all_z, last_back=last_back, white_back=white_back, max_depth=max_depth,
+                                    clamp_mode=clamp_mode)
+    return rgb, depth, weights, all_z
+
+
 def create_samples(N=512, voxel_origin=(0, 0, 0), cube_length=2.0):
     """extract_shapes.py:74-96 including the float-division index quirk (:84-86): the y and x voxel
     indices are computed with true division, so they are fractional."""

@@ -314,3 +314,46 @@ def test_mask2color_matches_reference_loop():
     wide = torch.randn(2, 51, 8, 8, generator=g).to(DEV)                   # the renderer's feat layout: logits are channels 32..50
     sl = wide[:, 32:51]
     assert torch.equal(seg_tools.mask2color(sl).cpu(), oops.mask2color(sl.cpu(), seg_tools.COLOR_MAP))
+
+
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_hierarchical_two_pass_matches_oracle_composition(precision):
+    """a8 wired: coarse fused pass -> ide3d_sample_pdf -> merged, sorted depths -> second fused pass (depths read from a tensor,
+    IDE3D_JITTER_ZVALS) vs the oracle's composition of the reference's own stages around sample_pdf
+    (volumetric_rendering.py:224-265), same injected uniforms for the stratified jitter and the importance draw."""
+    from ide3d_b200 import render
+    N, S, NI, res = 2, 24, 16, (8, 8)
+    tex, seg, dec, cam = _random_case(N, 32, seed=17)
+    g = torch.Generator().manual_seed(17)
+    u = torch.rand(N, 64, S, 1, generator=g)
+    ui = torch.rand(N * 64, NI, generator=g)
+    ro, do_, wo, zo = orr.render_frames_hierarchical(tex, seg, dec, cam, num_steps=S, n_importance=NI, resolution=res, jitter_u=u, importance_u=ui)
+    heads = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
+    feat, depth, w, z = render.raymarch_hierarchical(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=res, num_steps=S, n_importance=NI,
+                                                     jitter_u=u.to(DEV), importance_u=ui.to(DEV), return_weights=True, return_depths=True,
+                                                     precision=precision)
+    assert z.shape == (N, 64, S + NI) and bool((z[..., 1:] >= z[..., :-1]).all())
+    # the importance depths are a continuous function of the coarse weights: 1e-6-level weight differences move them by <= 1e-5
+    assert_close(z, zo.reshape(N, 64, S + NI), 2e-5, what='merged depths')
+    assert_close(feat, ro, 3 * FEAT_TOL[precision], what='feat'); assert_close(depth, do_, 3 * D_TOL[precision], what='depth')
+    assert_close(w, wo, 3 * W_TOL[precision], what='w')
+    # the importance samples concentrate where the coarse weights are: the merged set is not the stratified one
+    zc = render.coarse_depths(N, res, S, jitter_u=u.to(DEV), device=DEV)
+    assert_close(zc, orr.render_frames(tex, seg, dec, cam, num_steps=S, resolution=res, jitter_u=u, return_stages=True)['z_vals'].reshape(N, 64, S), 1e-6)
+    # det=True (no jitter anywhere) is reproducible
+    a = render.raymarch_hierarchical(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=res, num_steps=S, det=True, precision=precision)
+    b = render.raymarch_hierarchical(tex.to(DEV), seg.to(DEV), heads, cam.to(DEV), resolution=res, num_steps=S, det=True, precision=precision)
+    assert torch.equal(a[0], b[0]) and a[0].shape == (N, 64, 51)
+
+
+def test_hierarchical_flag_through_the_generator():
+    """rendering_kwargs / render_params 'hierarchical' reaches the renderer (forward only)."""
+    from ide3d_b200.compat import random_init_generator
+    G = random_init_generator(device=DEV, seed=0, img_resolution=128, plane_resolution=64, render_size=16, channel_max=32)
+    with torch.no_grad():
+        ws = G.mapping(torch.randn(1, G.z_dim, device=DEV), torch.zeros(1, 25, device=DEV))
+        c = torch.eye(4, device=DEV).reshape(1, 16); c[0, 11] = 2.7
+        c = torch.cat([c, torch.zeros(1, 9, device=DEV)], 1)
+        a = G.synthesis(ws, c=c, render_params=dict(num_steps=12), perturb=None)
+        b = G.synthesis(ws, c=c, render_params=dict(num_steps=12, hierarchical=True, n_importance=12), perturb=None)
+    assert a.shape == b.shape and torch.isfinite(b).all() and not torch.equal(a, b)

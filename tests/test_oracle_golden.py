@@ -210,3 +210,30 @@ def test_networks_restatement_loads_reference_state_dicts_and_reproduces_outputs
             xo, io, so = ms(T_('seg_x'), T_('seg_img').clone(), T_('seg_ws'), condition_img=T_('seg_seg').clone(), noise_mode='const')
             for got, key in ((xo, 'seg_out_x'), (io, 'seg_out_img'), (so, 'seg_out_seg')):
                 assert (got - T_(key)).abs().max() < 1e-5, (key, layout)
+
+
+def test_oracle_hierarchical_composition_properties():
+    """The two-pass composition around the pinned sample_pdf: merged depths ascending and inside [ray_start - h, ray_end + h],
+    S + n_importance samples per ray, weights a sub-probability; importance depths fall where the coarse weights are."""
+    import math
+    from oracle import camera as ocam, renderer as orr
+    g = torch.Generator().manual_seed(0)
+    tex = torch.nn.functional.interpolate(torch.randn(1, 96, 5, 5, generator=g), size=(16, 16), mode='bicubic', align_corners=True)
+    seg = torch.nn.functional.interpolate(torch.randn(1, 96, 5, 5, generator=g), size=(16, 16), mode='bicubic', align_corners=True)
+    dec = orr.Decoder.random(hidden=64, seed=2)
+    cam = torch.from_numpy(ocam.look_at_pose(np.array([[math.pi / 2]], np.float32), np.array([[math.pi / 2]], np.float32), [0, 0, 0.2], radius=2.7, batch_size=1))
+    S, NI = 12, 8
+    u = torch.rand(1, 16, S, 1, generator=g)
+    ui = torch.rand(16, NI, generator=g)
+    rgb, depth, w, z = orr.render_frames_hierarchical(tex, seg, dec, cam, num_steps=S, n_importance=NI, resolution=(4, 4), jitter_u=u, importance_u=ui)
+    assert z.shape == (1, 16, S + NI, 1) and w.shape == (1, 16, S + NI, 1) and rgb.shape == (1, 16, 51)
+    assert bool((z[:, :, 1:] >= z[:, :, :-1]).all())
+    h = (3.3 - 2.25) / (S - 1)
+    assert z.min() >= 2.25 - h and z.max() <= 3.3 + h
+    assert bool((w >= 0).all()) and float(w.sum(2).max()) <= 1 + 1e-5
+    st = orr.render_frames(tex, seg, dec, cam, num_steps=S, resolution=(4, 4), jitter_u=u, return_stages=True)
+    zc, wc = st['z_vals'].reshape(16, S), st['weights'].reshape(16, S)
+    # every importance depth lies in a bin (between two coarse midpoints) and bins with larger weight receive more of them on average
+    mids = 0.5 * (zc[:, :-1] + zc[:, 1:])
+    fine = orr.sample_pdf(mids, wc[:, 1:-1] + 1e-5, NI, u=ui)
+    assert bool((fine >= mids[:, :1]).all()) and bool((fine <= mids[:, -1:]).all())
