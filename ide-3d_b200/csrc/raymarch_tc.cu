@@ -40,10 +40,12 @@ constexpr int kStageBytes = 2 * kTileBytes;                              // hi +
 constexpr int kGroupCols = 256;                                          // TMEM columns per group: D1 3 x 64, D2 64
 constexpr int kD2Col = 64 * kTcMaxBlocks;
 constexpr int kUnitW = 4, kUnitH = 4, kTileDepth = 8;
-// register split (setmaxnreg): TEAMS = 3: 256 x 112 + 384 x 96 = 65536;  TEAMS = 2: 256 x 120 + 256 x 136 = 65536
+// register split (setmaxnreg): TEAMS = 2: 512 threads x 128 at launch -> consumers release down to 120, producers grow to 136
+// (256 x 120 + 256 x 136 = 65536).  TEAMS = 3: 640 threads x 96 at launch is the whole register file already; nobody can grow
+// (a setmaxnreg.inc with nothing released blocks forever -- measured: the first round-2 build hung exactly there), so no split.
 template <int TEAMS> struct TcCfg {
     static constexpr int kThreads = 32 * (kConsumerWarps + 4 * TEAMS);
-    static constexpr int kConsumerRegs = (TEAMS == 3) ? 112 : 120;
+    static constexpr int kConsumerRegs = (TEAMS == 3) ? 96 : 120;
     static constexpr int kProducerRegs = (TEAMS == 3) ? 96 : 136;
     static constexpr int kBaseRegs = (TEAMS == 3) ? 96 : 128;           // what __launch_bounds__(kThreads, 1) compiles to
 };
@@ -668,7 +670,7 @@ int launch_raymarch_tc(const ide3d_raymarch_params* p, bool channels_last, cudaS
     a.tiles_per_unit = ceil_div(p->num_steps, kTileDepth);
     // tuning knob: gather instruction shape
     a.ray_major = env_int("IDE3D_TC_RAY_MAJOR", 1, 0, 1);
-    const int teams = env_int("IDE3D_TC_TEAMS", 3, 2, kMaxTeams);
+    const int teams = env_int("IDE3D_TC_TEAMS", 2, 2, kMaxTeams);
     const int smem = 2 * a.prog.wpart + teams * kStageBytes + (kTcMaxBlocks * 64 + 64) * 4 + (2 * kMaxTeams + (2 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
     int grid = sm_count();
     if (grid * kGroups > a.num_units) grid = ceil_div(a.num_units, kGroups);

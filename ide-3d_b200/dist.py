@@ -106,20 +106,61 @@ def _pinned_buffer(shape, dtype):
     return buf
 
 
+_shared = {}
+
+
+def _shared_frame_buffer(shape, rank, world, tag):
+    """One uint8 frame buffer in /dev/shm that EVERY rank of the box maps (torch.from_file, shared) and page-locks
+    (cudaHostRegister): each GPU then downloads its own frames straight into rank 0's result over its own PCIe link -- no
+    collective, no second hop.  Cached per (shape, tag); rank 0 creates the file, one barrier makes it visible, and it is
+    unlinked as soon as everybody has it mapped (the mapping keeps it alive)."""
+    key = (tuple(shape), tag)
+    buf = _shared.get(key)
+    if buf is not None:
+        return buf
+    nbytes = 1
+    for d in shape:
+        nbytes *= int(d)
+    path = f"/dev/shm/ide3d_b200_{os.environ.get('MASTER_PORT', '0')}_{os.getuid()}_{tag}_{nbytes}.bin"
+    if rank == 0:
+        with open(path, 'wb') as f:
+            f.truncate(nbytes)
+    dist.barrier()
+    flat = torch.from_file(path, shared=True, size=nbytes, dtype=torch.uint8)
+    if torch.cuda.is_available():
+        rc = torch.cuda.cudart().cudaHostRegister(flat.data_ptr(), nbytes, 0)
+        if int(rc) != 0:
+            raise RuntimeError(f'ide3d_b200.dist: cudaHostRegister of the shared frame buffer failed ({rc})')
+    dist.barrier()
+    if rank == 0:
+        os.unlink(path)
+    buf = _shared[key] = flat.view(*shape)
+    return buf
+
+
 @torch.no_grad()
-def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, **synthesis_kwargs):
-    """The frame loop of gen_videos.py:127-139 as a pipeline: frames i = rank, rank+world, ... are rendered in batches;
-    every batch is gathered over the ranks (one all_gather of uint8 frames) and copied to page-locked HOST memory on a side
-    stream while the next batch renders.  ws [F, num_ws, w_dim], c [F, 25] on the host (pinned for asynchronous uploads).
-    Returns uint8 [F, 3, H, W] on the host on rank 0 (a cached pinned buffer unless `out` is given), None elsewhere.
-    F must be a multiple of world * batch."""
+def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, transport='auto', **synthesis_kwargs):
+    """The frame loop of gen_videos.py:127-139 as a pipeline: frames i = rank, rank+world, ... are rendered in batches and
+    copied to page-locked HOST memory on a side stream while the next batch renders.  ws [F, num_ws, w_dim], c [F, 25] on
+    the host (pinned for asynchronous uploads).  Returns uint8 [F, 3, H, W] on the host on rank 0, None elsewhere.
+    F must be a multiple of world * batch.
+
+    transport (world > 1; how the frames of the other ranks reach rank 0's host memory):
+      'shm'   every rank downloads its own frames into ONE shared, page-locked /dev/shm buffer (all ranks on one box): `world`
+              PCIe links in parallel, ranks never wait for each other inside the loop, one barrier at the end.  Default on CUDA.
+      'nccl'  one all_gather of the batch's uint8 frames per batch on the compute stream, rank 0 downloads everything (the
+              round-1 path; also what the gloo CPU tests exercise, and the only choice across boxes)."""
     F = ws.shape[0]
     assert F % (world * batch) == 0, 'stream_frames_sharded: F must be a multiple of world * batch'
     dev = next(G.parameters()).device
     cuda = dev.type == 'cuda'
+    if transport == 'auto':
+        transport = 'shm' if (cuda and world > 1 and os.path.isdir('/dev/shm')) else 'nccl'
     shape = (F, G.img_channels, G.img_resolution, G.img_resolution)
     host = None
-    if rank == 0:
+    if world > 1 and transport == 'shm':
+        host = _shared_frame_buffer(shape, rank, world, 'frames')
+    elif rank == 0:
         host = out if out is not None else _pinned_buffer(shape, torch.uint8)
     copy_stream = torch.cuda.Stream(dev) if cuda else None
     per_rank = F // world
@@ -133,6 +174,18 @@ def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, **synthesis_
         if isinstance(img, (tuple, list)):
             img = img[0]
         img = (img * 127.5 + 128).clamp(0, 255).to(torch.uint8).contiguous()
+        if world > 1 and transport == 'shm':
+            # my frames k of this batch are global frames rank + world * (b0 + k): one asynchronous copy per frame into the shared buffer
+            if cuda:
+                copy_stream.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(copy_stream):
+                    for k in range(batch):
+                        host[rank + world * (b0 + k)].copy_(img[k], non_blocking=True)
+                img.record_stream(copy_stream)
+            else:
+                for k in range(batch):
+                    host[rank + world * (b0 + k)].copy_(img[k])
+            continue
         if world > 1:
             allf = torch.empty((world,) + tuple(img.shape), dtype=img.dtype, device=dev)
             dist.all_gather_into_tensor(allf.view((world * img.shape[0],) + tuple(img.shape[1:])), img)
@@ -150,6 +203,13 @@ def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, **synthesis_
         if copy_stream is not None:
             copy_stream.synchronize()
         torch.cuda.current_stream(dev).synchronize()
+    if world > 1 and transport == 'shm':
+        dist.barrier()                                   # every rank's frames are in the shared buffer
+        if rank != 0:
+            return None
+        if out is not None:
+            out.copy_(host)
+            return out
     return host
 
 

@@ -34,7 +34,8 @@ def _decoder_from_renderer(r):
 
 def _renderer_forward(self, img_v, seg_v, cam2world, img_size=64, num_steps=48, fov=18.0, ray_start=2.25, ray_end=3.3,
                       nerf_noise=0.0, perturb='hash', jitter_u=None, seed=None, clamp_mode='softplus', last_back=False,
-                      white_back=False, max_depth=None, fill_mode=None, return_weights=False):
+                      white_back=False, max_depth=None, fill_mode=None, return_weights=False, hierarchical=False, n_importance=None,
+                      importance_u=None):
     res = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
     n = img_v.shape[0]
     if jitter_u is None and perturb == 'rand':
@@ -46,6 +47,15 @@ def _renderer_forward(self, img_v, seg_v, cam2world, img_size=64, num_steps=48, 
     if jitter_u is not None:
         jitter_u = jitter_u.reshape(n, res[0] * res[1], num_steps, 1).cpu()
     noise = torch.randn([n, res[0] * res[1], num_steps, 1]) if nerf_noise else None
+    if hierarchical:
+        assert not nerf_noise and fill_mode is None, 'oracle: hierarchical composition is defined without density noise / fill modes'
+        rgb, depth, w, _ = orr.render_frames_hierarchical(
+            img_v.float().cpu().contiguous(), seg_v.float().cpu().contiguous(), _decoder_from_renderer(self),
+            cam2world.float().cpu().reshape(n, 4, 4), fov=fov, num_steps=num_steps, n_importance=n_importance, ray_start=ray_start,
+            ray_end=ray_end, resolution=res, box_scale=self.box_scale, jitter_u=jitter_u, jitter_seed=seed,
+            importance_u=None if importance_u is None else importance_u.cpu(), det=perturb in (None, False, 'none'),
+            clamp_mode=clamp_mode, last_back=last_back, white_back=white_back, max_depth=max_depth)
+        return rgb, depth, (w if return_weights else None)
     rgb, depth, w = orr.render_frames(img_v.float().cpu().contiguous(), seg_v.float().cpu().contiguous(),
                                       _decoder_from_renderer(self), cam2world.float().cpu().reshape(n, 4, 4), fov=fov,
                                       num_steps=num_steps, ray_start=ray_start, ray_end=ray_end, resolution=res,

@@ -56,6 +56,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--small', action='store_true')
     ap.add_argument('--no-ref', action='store_true', help='skip the reference plugins (baseline/_ref)')
+    ap.add_argument('--only', default=None, help='substring filter on the op name')
     args = ap.parse_args()
     C = 64 if args.small else 512
     pk = peak()
@@ -79,6 +80,8 @@ def main():
             if layout == 'channels_last':
                 x = x.contiguous(memory_format=torch.channels_last)
             for name, fn in cases.items():
+                if args.only and args.only not in name:
+                    continue
                 try:
                     ms, y = timeit(lambda: fn(ours))
                 except Exception as e:          # noqa
@@ -102,6 +105,8 @@ def main():
 
     # ---- the fused forms on the shapes of the synthesis step (NHWC fp32, batch 8): algorithmic bytes = every tensor once
     def fused_case(name, fn, nbytes):
+        if args.only and args.only not in name:
+            return
         try:
             ms, y = timeit(fn)
         except Exception as e:          # noqa

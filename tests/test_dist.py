@@ -32,6 +32,9 @@ def _worker(rank, world, port, q):
         # streaming variant (the e2e leg of bench.py): F multiple of world * batch, result on the host of rank 0 only
         streamed = idist.stream_frames_sharded(G, ws[:4], c[:4], rank, world, batch=2, num_steps=6, perturb=None)
         sdiff = int((streamed.int() - single[:4].int()).abs().max()) if rank == 0 else (0 if streamed is None else 99)
+        # the shared-memory transport (default on CUDA boxes): every rank writes its own frames into one /dev/shm buffer
+        shm = idist.stream_frames_sharded(G, ws[:4], c[:4], rank, world, batch=2, transport='shm', num_steps=6, perturb=None)
+        sdiff = max(sdiff, int((shm.int() - single[:4].int()).abs().max()) if rank == 0 else (0 if shm is None else 99))
     # voxel slabs: every rank fills its contiguous slab of a fake sigma volume, one all_gather restores the volume
     total = 4 ** 3 + 1
     first, count = idist.slab_range(total, rank, world)
