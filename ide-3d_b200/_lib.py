@@ -37,6 +37,12 @@ class FirEpilogue(C.Structure):
                 ('act', C.c_int), ('alpha', C.c_float), ('gain', C.c_float), ('clamp', C.c_float), ('noise_batch', C.c_int64)]
 
 
+class StyleLayer(C.Structure):
+    _fields_ = [('affine_w', C.c_void_p), ('affine_b', C.c_void_p), ('wsq', C.c_void_p), ('w_gain', C.c_float), ('b_gain', C.c_float),
+                ('out_scale', C.c_float), ('w_index', C.c_int), ('in_ch', C.c_int), ('out_ch', C.c_int),
+                ('style_off', C.c_int64), ('dcoef_off', C.c_int64)]
+
+
 class FlreluParams(C.Structure):
     _fields_ = [('x', C.c_void_p), ('b', C.c_void_p), ('fu', C.c_void_p), ('fd', C.c_void_p), ('y', C.c_void_p),
                 ('s', C.c_void_p), ('dtype', C.c_int), ('up', C.c_int), ('down', C.c_int),
@@ -148,9 +154,10 @@ def get_lib():
     lib.ide3d_mask2color.argtypes = [vp, i32, i32, i32, i32, i64, i64, i64, i64, vp, vp, i32, vp]
     lib.ide3d_integrate.argtypes = [vp, vp, vp, vp, f32, i32, i32, i32, i32, i32, i32, i32, f32, i32, vp, vp, vp, vp]
     lib.ide3d_sample_pdf.argtypes = [vp, vp, vp, i32, i32, i32, f32, vp, vp]
+    lib.ide3d_style_plan.argtypes = [vp, i32, i32, i32, C.POINTER(StyleLayer), i32, vp, vp, vp]
     for name in ('bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_act', 'raymarch_fwd', 'sample_voxel',
                  'sigma_grid', 'planes_to_nhwc', 'initial_rays', 'transform_points', 'sample_triplane', 'integrate',
-                 'sample_pdf', 'abi_version'):
+                 'sample_pdf', 'style_plan', 'abi_version'):
         getattr(lib, 'ide3d_' + name).restype = C.c_int
     if lib.ide3d_abi_version() != 1:
         raise RuntimeError('ide3d_b200: ABI version mismatch between _lib.py and libide3d_b200.so')
@@ -164,7 +171,7 @@ def exported_symbols():
             'ide3d_upfirdn2d', 'ide3d_upfirdn2d_add', 'ide3d_upfirdn2d_epilogue',
             'ide3d_filtered_lrelu', 'ide3d_filtered_lrelu_act', 'ide3d_raymarch_fwd', 'ide3d_sample_voxel',
             'ide3d_sigma_grid', 'ide3d_planes_to_nhwc', 'ide3d_initial_rays', 'ide3d_transform_points',
-            'ide3d_sample_triplane', 'ide3d_integrate', 'ide3d_sample_pdf', 'ide3d_mask2color']
+            'ide3d_sample_triplane', 'ide3d_integrate', 'ide3d_sample_pdf', 'ide3d_mask2color', 'ide3d_style_plan']
 
 
 def check(rc, allow_unsupported=False):

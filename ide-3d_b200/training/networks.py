@@ -26,6 +26,7 @@ FUSED_MODCONV_MIN_RES = 1 << 30      # block resolutions >= this use the grouped
 # anyway.  The reference only does this for its fp16 layers (inversion/networks.py:746).  IDE3D_CHANNELS_LAST=0 restores
 # the reference's NCHW fp32 layout (same values).
 CHANNELS_LAST = os.environ.get('IDE3D_CHANNELS_LAST', '1') != '0'
+STYLE_PLAN = os.environ.get('IDE3D_STYLE_PLAN', '1') != '0'      # styles + demodulation coefficients of a whole synthesis call in two launches (StylePlan)
 CHAIN_MODULATION = True              # epilogues also write the next layer's `x * styles` (SynthesisBlock._features)
 # 1x1 convolutions of NHWC activations as one [N*H*W, I] x [I, O] matrix product (cuBLASLt, tf32 exactly when the cuDNN convolution
 # it replaces would use tf32) instead of cuDNN's conv3d_fprop kernels, which stream these shapes at ~40 % of the HBM peak.
@@ -51,7 +52,7 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True, epilogue=None, premodulated=False):
+                     flip_weight=True, fused_modconv=True, epilogue=None, premodulated=False, dcoefs=None):
     """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I].
     epilogue (activation-scaled path only): dict(b, act, gain, clamp) -- the bias_act that always follows (:512, :707) is
     then applied here, fused with the demodulation / noise pass (`bias_act.scaled_bias_act`); optional keys next_scale /
@@ -62,12 +63,15 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     if x.dtype == torch.float16 and demodulate:      # keep fp16 in range (:78-81)
         weight = weight * (1 / np.sqrt(in_channels * kh * kw) / weight.norm(float('inf'), dim=[1, 2, 3], keepdim=True))
         styles = styles / styles.norm(float('inf'), dim=1, keepdim=True)
-    w = dcoefs = None
+    w = None
     if fused_modconv:
+        dcoefs = None
         w = weight.unsqueeze(0) * styles.reshape(batch_size, 1, -1, 1, 1)            # [N,O,I,k,k]
     if demodulate and fused_modconv:
         dcoefs = (w.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt()                       # [N,O]
         w = w * dcoefs.reshape(batch_size, -1, 1, 1, 1)
+    elif demodulate and dcoefs is not None:
+        pass                                        # precomputed for the whole synthesis call (StylePlan below)
     elif demodulate:
         # sum_{i,k} (W[o,i,k] s[n,i])^2 = sum_i s[n,i]^2 sum_k W[o,i,k]^2 : a [N,I] x [I,O] product instead of
         # materialising the [N,O,I,k,k] modulated weight just to reduce it (same value up to fp32 summation order)
@@ -214,7 +218,7 @@ class SynthesisLayer(torch.nn.Module):
         self.bias = torch.nn.Parameter(torch.zeros([out_channels]))
 
     def forward(self, x, w, noise_mode='random', fused_modconv=True, gain=1, styles=None, premodulated=False, next_styles=None,
-                only_next=False):
+                only_next=False, dcoefs=None):
         """styles / premodulated / next_styles / only_next: block-internal chaining of activation-scaled layers -- the
         epilogue of this layer can already write `y * next_styles` for the layer that follows (see SynthesisBlock._features)."""
         assert noise_mode in ['random', 'const', 'none']
@@ -232,7 +236,7 @@ class SynthesisLayer(torch.nn.Module):
             epilogue.update(next_scale=next_styles, only_next=only_next)
         return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                 resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
-                                epilogue=epilogue, premodulated=premodulated)
+                                epilogue=epilogue, premodulated=premodulated, dcoefs=None if fused_modconv else dcoefs)
 
 
 @persistence.persistent_class
@@ -291,6 +295,7 @@ class SynthesisBlock(torch.nn.Module):
         self.num_torgb += 1
 
     def _features(self, x, ws, force_fp32, fused_modconv, layer_kwargs):
+        layer_kwargs = dict(layer_kwargs)
         misc.assert_shape(ws, [None, self.num_conv + self.num_torgb, self.w_dim])
         w_iter = iter(ws.unbind(dim=1))
         dtype = torch.float16 if self.use_fp16 and not force_fp32 else torch.float32
@@ -315,13 +320,19 @@ class SynthesisBlock(torch.nn.Module):
             x = x.to(dtype=dtype, memory_format=memory_format)
             w0, w1 = next(w_iter), next(w_iter)
         w_rgb = next(w_iter)
+        plan = layer_kwargs.pop('style_plan', None) if chain else None
+        layer_kwargs.pop('style_plan', None)
         if chain:
-            s1, s_rgb = self.conv1.affine(w1), self.torgb.styles(w_rgb)
+            if plan is not None:                       # every style / demodulation coefficient of the call was computed up front
+                (s1, d1), (s_rgb, _) = plan[self.conv1], plan[self.torgb]
+                s0, d0 = plan[self.conv0] if self.in_channels != 0 else (None, None)
+            else:
+                s1, s_rgb, s0, d0, d1 = self.conv1.affine(w1), self.torgb.styles(w_rgb), None, None, None
             pre = False
             if self.in_channels != 0:
-                x = self.conv0(x, w0, fused_modconv=False, next_styles=s1, only_next=True, **layer_kwargs)
+                x = self.conv0(x, w0, fused_modconv=False, styles=s0, dcoefs=d0, next_styles=s1, only_next=True, **layer_kwargs)
                 pre = True
-            x, x_rgb = self.conv1(x, w1, fused_modconv=False, styles=s1, premodulated=pre, next_styles=s_rgb, **layer_kwargs)
+            x, x_rgb = self.conv1(x, w1, fused_modconv=False, styles=s1, dcoefs=d1, premodulated=pre, next_styles=s_rgb, **layer_kwargs)
             rgb_in = (x_rgb, s_rgb)
         else:
             if self.in_channels != 0:
@@ -384,3 +395,69 @@ class SegSynthesisBlock(SynthesisBlock):
         img = self._accumulate(img, y[:, :self.img_channels])
         seg = self._accumulate(condition_img, y[:, self.img_channels:])
         return x, img, seg
+
+
+class StylePlan:
+    """Styles and demodulation coefficients of every modulated convolution of a synthesis network in two kernel launches
+    (ide3d_style_plan) instead of ~8 library launches per layer.  Built once per network; holds fp32 device copies of the constants
+    (sum_k W^2 per layer) keyed on the parameters' versions.  `run(ws)` -> {layer module: (styles [N, I], dcoefs [N, O] | None)}.
+    Inference only, fp32, activation-scaled (not weight-modulated) convolutions -- SynthesisBlock._features decides."""
+
+    def __init__(self, blocks_with_base):
+        """blocks_with_base: [(SynthesisBlock, index of the block's first w in ws)] in ws order."""
+        self.entries = []                       # (layer, w_index, demodulate, out_scale)
+        for block, base in blocks_with_base:
+            j = base
+            if block.in_channels != 0:
+                self.entries.append((block.conv0, j, True, 1.0)); j += 1
+            self.entries.append((block.conv1, j, True, 1.0)); j += 1
+            self.entries.append((block.torgb, j, False, float(block.torgb.weight_gain)))
+        assert len(self.entries) <= 32
+        self._key = None
+        self._consts = None
+
+    def _constants(self, device):
+        params = [p for layer, *_ in self.entries for p in (layer.affine.weight, layer.affine.bias, layer.weight)]
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in params)
+        if key == self._key:
+            return self._consts
+        from .. import _lib as L
+        keep, structs = [], (L.StyleLayer * len(self.entries))()
+        s_off = d_off = 0
+        for k, (layer, w_index, demod, out_scale) in enumerate(self.entries):
+            aw = layer.affine.weight.detach().to(device=device, dtype=torch.float32).contiguous()
+            ab = layer.affine.bias.detach().to(device=device, dtype=torch.float32).contiguous()
+            o, i = layer.weight.shape[0], layer.weight.shape[1]
+            wsq = layer.weight.detach().to(device=device, dtype=torch.float32).square().sum(dim=[2, 3]).contiguous() if demod else None
+            keep += [aw, ab, wsq]
+            structs[k] = L.StyleLayer(aw.data_ptr(), ab.data_ptr(), wsq.data_ptr() if demod else None, float(layer.affine.weight_gain),
+                                      float(layer.affine.bias_gain), float(out_scale), int(w_index), int(i), int(o), 0, 0)
+            structs[k].style_off, structs[k].dcoef_off = s_off, d_off        # per-sample offsets; scaled by N in run()
+            s_off += i
+            d_off += o if demod else 0
+        self._key, self._consts = key, (keep, structs, s_off, d_off)
+        return self._consts
+
+    @torch.no_grad()
+    def run(self, ws):
+        import ctypes as C
+        from .. import _lib as L
+        ws = ws.detach().to(torch.float32).contiguous()
+        n, num_ws, w_dim = ws.shape
+        _, base, s_tot, d_tot = self._constants(ws.device)
+        structs = (L.StyleLayer * len(self.entries))()
+        for k in range(len(self.entries)):
+            C.memmove(C.byref(structs[k]), C.byref(base[k]), C.sizeof(L.StyleLayer))
+            structs[k].style_off, structs[k].dcoef_off = base[k].style_off * n, base[k].dcoef_off * n
+        styles = torch.empty(n * s_tot, dtype=torch.float32, device=ws.device)
+        dcoefs = torch.empty(max(1, n * d_tot), dtype=torch.float32, device=ws.device)
+        with torch.cuda.device(ws.device):
+            L.check(L.get_lib().ide3d_style_plan(L.ptr(ws), n, num_ws, w_dim, structs, len(self.entries), L.ptr(styles), L.ptr(dcoefs),
+                                                 L.stream_ptr(ws.device)))
+        out = {}
+        for k, (layer, _, demod, _) in enumerate(self.entries):
+            i, o = structs[k].in_ch, structs[k].out_ch
+            s = styles[structs[k].style_off:structs[k].style_off + n * i].view(n, i)
+            d = dcoefs[structs[k].dcoef_off:structs[k].dcoef_off + n * o].view(n, o) if demod else None
+            out[layer] = (s, d)
+        return out

@@ -19,6 +19,8 @@ world->plane scale 2/box_warp, stratified jitter by counter-hash, SR widths (128
 """
 
 import math
+import os
+import weakref
 
 import numpy as np
 import torch
@@ -29,6 +31,7 @@ from . import networks
 from .networks import FullyConnectedLayer, MappingNetwork, SegSynthesisBlock, SynthesisBlock
 
 N_FEAT, N_SEG, N_OUT = 32, 19, 52
+_STYLE_PLANS = weakref.WeakKeyDictionary()
 
 
 # ================================================================================================ decoder
@@ -188,6 +191,23 @@ class SynthesisNetwork(torch.nn.Module):
             idx += b.num_conv
         return voxel_ws, block_ws
 
+    def _style_plan(self, ws):
+        """All styles / demodulation coefficients of the call in two launches (networks.StylePlan) when the blocks run the fp32
+        activation-scaled inference path on a CUDA device; None otherwise (every layer then computes its own, as the reference does)."""
+        if not (networks.STYLE_PLAN and ws.is_cuda) or (torch.is_grad_enabled() and (ws.requires_grad or any(p.requires_grad for p in self.parameters()))):
+            return None
+        blocks = [getattr(self, f'vb{r}') for r in self.voxel_block_resolutions] + [getattr(self, f'b{r}') for r in self.block_resolutions]
+        if any(b.use_fp16 for b in blocks) or int(os.environ.get('IDE3D_FUSED_MODCONV_MIN_RES', networks.FUSED_MODCONV_MIN_RES)) <= max(b.resolution for b in blocks):
+            return None
+        plan = _STYLE_PLANS.get(self)                 # kept outside the module: the plan holds ctypes structs and is not picklable
+        if plan is None:
+            pairs, idx = [], 0
+            for b in blocks:
+                pairs.append((b, idx))
+                idx += b.num_conv
+            plan = _STYLE_PLANS[self] = networks.StylePlan(pairs)
+        return plan.run(ws)
+
     def backbone(self, voxel_ws, **block_kwargs):
         x = img_v = seg_v = None
         for res, cur_ws in zip(self.voxel_block_resolutions, voxel_ws):
@@ -209,6 +229,9 @@ class SynthesisNetwork(torch.nn.Module):
                 return_raw=False, return_dict=False, fused_modconv=None, **render_overrides):
         voxel_ws, block_ws = self.split_ws(ws)
         block_kwargs = dict(noise_mode=noise_mode, force_fp32=force_fp32, fused_modconv=fused_modconv)
+        plan = self._style_plan(ws)
+        if plan is not None:
+            block_kwargs['style_plan'] = plan
         img_v, seg_v = self.backbone(voxel_ws, **block_kwargs)
 
         kw = dict(self.rendering_kwargs)

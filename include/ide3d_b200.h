@@ -294,6 +294,25 @@ int ide3d_sample_pdf(const float* bins, const float* weights, const float* u, in
 int ide3d_mask2color(const float* masks, int n, int c, int h, int w, int64_t stride_n, int64_t stride_c, int64_t stride_h,
                      int64_t stride_w, const float* lut, void* out, int out_u8, ide3d_stream_t stream);
 
+/* Style vectors and demodulation coefficients of every modulated convolution of one synthesis call, two launches
+ * (replaces per layer: FullyConnectedLayer.forward of the affine, inversion/networks.py:136-165 / :476, and the dcoefs
+ * reduction of modulated_conv2d, :89-90).
+ *   styles[style_off + n*in_ch + i] = ((affine_w[i,:] . ws[n, w_index, :]) * w_gain + affine_b[i] * b_gain) * out_scale
+ *   dcoefs[dcoef_off + n*out_ch + o] = rsqrt(sum_i styles[n,i]^2 * wsq[o,i] + 1e-8)        (layers with wsq != NULL)
+ * ws [n, num_ws, w_dim] fp32 dense; wsq[o,i] = sum over the kernel taps of weight[o,i,:,:]^2 (a constant of the weights). */
+typedef struct ide3d_style_layer {
+    const float* affine_w;      /* [in_ch, w_dim] */
+    const float* affine_b;      /* [in_ch] or NULL */
+    const float* wsq;           /* [out_ch, in_ch] or NULL (no demodulation: ToRGB) */
+    float w_gain, b_gain;       /* FullyConnectedLayer runtime gains */
+    float out_scale;            /* extra factor on the style (ToRGB weight_gain), 1 otherwise */
+    int w_index;                /* which ws[:, w_index] feeds the layer */
+    int in_ch, out_ch;
+    int64_t style_off, dcoef_off;
+} ide3d_style_layer;
+int ide3d_style_plan(const float* ws, int n, int num_ws, int w_dim, const ide3d_style_layer* layers, int num_layers,
+                     float* styles, float* dcoefs, ide3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

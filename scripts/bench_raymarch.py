@@ -44,14 +44,16 @@ def main():
 
     base = None
     variants = [('v1 (round 1)', dict(IDE3D_TC_V1='1'))]
-    for teams in ('3', '2'):
-        for rm in ('1', '0'):
-            variants.append((f'v2 teams={teams} ray_major={rm}', dict(IDE3D_TC_V1='0', IDE3D_TC_TEAMS=teams, IDE3D_TC_RAY_MAJOR=rm)))
+    for teams in ('2',):
+        variants.append((f'v3 teams={teams}', dict(IDE3D_TC_V1='0', IDE3D_TC_V2='0', IDE3D_TC_TEAMS=teams, IDE3D_TC_RAY_MAJOR='1')))
+    for teams in ('2',):
+        for rm in ('1',):
+            variants.append((f'v2 teams={teams} ray_major={rm}', dict(IDE3D_TC_V1='0', IDE3D_TC_V2='1', IDE3D_TC_TEAMS=teams, IDE3D_TC_RAY_MAJOR=rm)))
     only = [a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--only=')]
     for name, env in variants:
         if only and not any(o in name for o in only):
             continue
-        for k in ('IDE3D_TC_V1', 'IDE3D_TC_TEAMS', 'IDE3D_TC_RAY_MAJOR'):
+        for k in ('IDE3D_TC_V1', 'IDE3D_TC_V2', 'IDE3D_TC_TEAMS', 'IDE3D_TC_RAY_MAJOR'):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:

@@ -9,6 +9,7 @@ epilogues and the optional matmul form of the 1x1 convolutions."""
 import pytest
 import torch
 
+from conftest import assert_close
 from oracle.backend import cpu_reference_ops
 
 pytestmark = pytest.mark.gpu
@@ -116,3 +117,46 @@ def test_stream_frames_matches_batch_loop_and_lands_in_pinned_host_memory(case):
     # profiles/r02a_parity_fullsize_and_determinism.txt: every stage is run-to-run bit-equal under all cudnn.benchmark /
     # cudnn.deterministic settings; the one-level difference seen in round 1 came from comparing DIFFERENT batch sizes, above)
     assert torch.equal(streamed[:2], streamed[2:])
+
+
+def test_style_plan_matches_per_layer_styles():
+    """networks.StylePlan (ide3d_style_plan: every style vector and demodulation coefficient of the call in two launches) against the
+    per-layer computation it replaces (FullyConnectedLayer affine + the dcoefs reduction of modulated_conv2d): same values, same image."""
+    from ide3d_b200.compat import random_init_generator
+    from ide3d_b200.training import networks
+    G = random_init_generator(device='cuda', seed=3, img_resolution=128, plane_resolution=64, render_size=16, channel_max=64)
+    torch.manual_seed(0)
+    # non-trivial affine biases / noise strengths so that every term of the formula is exercised
+    with torch.no_grad():
+        for m in G.synthesis.modules():
+            if isinstance(m, (networks.SynthesisLayer, networks.ToRGBLayer)):
+                m.affine.bias.add_(0.3 * torch.randn_like(m.affine.bias))
+    z = torch.randn(3, G.z_dim, device='cuda')
+    c = torch.eye(4, device='cuda').reshape(1, 16).repeat(3, 1); c[:, 11] = 2.7
+    c = torch.cat([c, torch.zeros(3, 9, device='cuda')], 1)
+    with torch.no_grad():
+        ws = G.mapping(z, c)
+        ws = ws + 0.1 * torch.randn_like(ws)                      # a different w per layer
+        plan = G.synthesis._style_plan(ws)
+        assert plan is not None
+        voxel_ws, block_ws = G.synthesis.split_ws(ws)
+        blocks = [getattr(G.synthesis, f'vb{r}') for r in G.synthesis.voxel_block_resolutions] + [getattr(G.synthesis, f'b{r}') for r in G.synthesis.block_resolutions]
+        for blk, bws in zip(blocks, voxel_ws + block_ws):
+            w_iter = iter(bws.unbind(1))
+            layers = ([blk.conv0] if blk.in_channels != 0 else []) + [blk.conv1]
+            for layer in layers:
+                w = next(w_iter)
+                s_ref = layer.affine(w)
+                d_ref = (s_ref.square() @ layer.weight.square().sum(dim=[2, 3]).t() + 1e-8).rsqrt()
+                s, d = plan[layer]
+                assert_close(s, s_ref, 1e-5 * float(s_ref.abs().max()), what='styles'); assert_close(d, d_ref, 1e-5 * float(d_ref.abs().max()), what='dcoefs')
+            s, d = plan[blk.torgb]
+            assert d is None
+            assert_close(s, blk.torgb.styles(next(w_iter)), 1e-6, what='torgb styles')
+        a = G.synthesis(ws, c=c, perturb=None)
+        saved, networks.STYLE_PLAN = networks.STYLE_PLAN, False
+        try:
+            b = G.synthesis(ws, c=c, perturb=None)
+        finally:
+            networks.STYLE_PLAN = saved
+    assert_close(a, b, 2e-5 * float(b.abs().max()), what='image with / without the style plan')
