@@ -132,7 +132,7 @@ def get_lib():
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(f'ide3d_b200: CUDA library not built ({LIB_PATH} missing); run '
                            f'`python {os.path.join(_HERE, "build.py")}` -- there is no CPU fallback')
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(LIB_PATH, mode=os.RTLD_NOW)       # every symbol resolved at load: a half-built library fails here, loudly
     lib.ide3d_last_error.restype = C.c_char_p
     lib.ide3d_launch_count.restype = C.c_uint64
     vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float

@@ -18,7 +18,7 @@ CSRC = os.path.join(HERE, 'csrc')
 OBJ = os.path.join(HERE, '_build')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libide3d_b200.so')
-UNITS = ['capi', 'raymarch', 'raymarch_tc', 'raymarch_tc3', 'raymarch_tc_v1', 'voxel', 'stages', 'style_plan', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
+UNITS = ['capi', 'raymarch', 'raymarch_tc', 'raymarch_tc3', 'raymarch_tc_v1', 'voxel', 'voxel_tc', 'stages', 'style_plan', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
 NVCC_FLAGS = ['-O3', '-std=c++17', '--expt-relaxed-constexpr', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-lineinfo', '-Xcompiler', '-fPIC', '-Xptxas', '-v']
 

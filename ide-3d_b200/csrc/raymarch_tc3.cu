@@ -32,10 +32,11 @@ constexpr int kIssuerWarps = 4;                     // one warpgroup: warps 0 / 
 template <int TEAMS> struct Cfg {
     static constexpr int kThreads = 32 * (kConsumerWarps + 4 * TEAMS + kIssuerWarps);
     // launch: 640 x 96 (TEAMS = 2).  issuers release down to 40, consumers to 88, producers grow to 128: 5120 + 22528 + 32768 <= 61440
+    //         768 x 80 (TEAMS = 3).  issuers 40, consumers 72, producers 96: 5120 + 18432 + 36864 <= 61440
     static constexpr int kBaseRegs = (TEAMS == 2) ? 96 : 80;
     static constexpr int kIssuerRegs = 40;
-    static constexpr int kConsumerRegs = (TEAMS == 2) ? 88 : 80;
-    static constexpr int kProducerRegs = (TEAMS == 2) ? 128 : 80;
+    static constexpr int kConsumerRegs = (TEAMS == 2) ? 88 : 72;
+    static constexpr int kProducerRegs = (TEAMS == 2) ? 128 : 96;
 };
 
 struct Args3 {
@@ -426,7 +427,9 @@ static bool tc3_eligible(tc3::Args3& A) {
 int launch_raymarch_tc3(const TcArgs& a, int teams, cudaStream_t st, bool& handled) {
     tc3::Args3 A;
     A.a = a;
-    handled = (teams == 2) && tc3_eligible(A);          // the three-team variant lives in raymarch_tc.cu only
+    // (the three-team instantiation passes the small parity cases but does not finish at the full-size configuration -- not root-caused;
+    //  IDE3D_TC_TEAMS=3 therefore selects the raymarch_tc.cu kernel)
+    handled = (teams == 2) && tc3_eligible(A);
     if (!handled) return IDE3D_OK;
     const int smem = 2 * a.prog.wpart + teams * kStageBytes + (kTcMaxBlocks * 64 + 64 + 64) * 4 + (2 * kMaxTeams + (6 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
     int grid = sm_count();

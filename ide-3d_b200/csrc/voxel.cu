@@ -166,6 +166,11 @@ static int fill_common(VoxelArgs& a, const ide3d_triplane* tex, const ide3d_trip
     return IDE3D_OK;
 }
 
+// voxel_tc.cu: sigma-only queries on the tensor cores (decoders with a density head over the shape planes, channels-last planes)
+int launch_sigma_tc(const ide3d_triplane& seg, const ide3d_decoder& dec, const float* points, long long P, int n, float box_scale,
+                    float* out, int grid_mode, int grid_n, float voxel_size, float org_x, float org_y, float org_z, float pre_scale,
+                    long long first, cudaStream_t st, bool& handled);
+
 }  // namespace ide3d
 
 using namespace ide3d;
@@ -181,6 +186,11 @@ extern "C" int ide3d_sample_voxel(const ide3d_triplane* tex, const ide3d_triplan
     if (num_points == 0) return IDE3D_OK;
     IDE3D_REQUIRE(points && out, "sample_voxel: null points/out");
     a.points = points; a.P = num_points; a.box_scale = box_scale; a.sigma_only = sigma_only; a.out = out;
+    if (sigma_only && cl) {
+        bool handled = false;
+        rc = launch_sigma_tc(*seg, *dec, points, num_points, a.n, box_scale, out, 0, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0, (cudaStream_t)stream, handled);
+        if (handled) return rc;
+    }
     return dispatch_voxel<false>(a, cl, kind, (cudaStream_t)stream);
 }
 
@@ -205,6 +215,12 @@ extern "C" int ide3d_sigma_grid(const ide3d_triplane* tex, const ide3d_triplane*
     a.org_z = (float)((double)voxel_origin[2] - half);
     a.pre_scale = pre_scale;
     a.first = first; a.P = count; a.box_scale = box_scale; a.sigma_only = 1; a.out = out; a.points = nullptr;
+    if (cl) {
+        bool handled = false;
+        rc = launch_sigma_tc(*seg, *dec, nullptr, count, a.n, box_scale, out, 1, grid_n, a.voxel_size, a.org_x, a.org_y, a.org_z, pre_scale,
+                             first, (cudaStream_t)stream, handled);
+        if (handled) return rc;
+    }
     return dispatch_voxel<true>(a, cl, kind, (cudaStream_t)stream);
 }
 

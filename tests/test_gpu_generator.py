@@ -131,6 +131,7 @@ def test_style_plan_matches_per_layer_styles():
         for m in G.synthesis.modules():
             if isinstance(m, (networks.SynthesisLayer, networks.ToRGBLayer)):
                 m.affine.bias.add_(0.3 * torch.randn_like(m.affine.bias))
+    saved_tf32, torch.backends.cudnn.allow_tf32 = torch.backends.cudnn.allow_tf32, False      # TF32 convolutions amplify 1e-7 input differences to 1e-3
     z = torch.randn(3, G.z_dim, device='cuda')
     c = torch.eye(4, device='cuda').reshape(1, 16).repeat(3, 1); c[:, 11] = 2.7
     c = torch.cat([c, torch.zeros(3, 9, device='cuda')], 1)
@@ -159,4 +160,5 @@ def test_style_plan_matches_per_layer_styles():
             b = G.synthesis(ws, c=c, perturb=None)
         finally:
             networks.STYLE_PLAN = saved
+            torch.backends.cudnn.allow_tf32 = saved_tf32
     assert_close(a, b, 2e-5 * float(b.abs().max()), what='image with / without the style plan')
