@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/ide3d_b200.h"
 
@@ -40,6 +41,17 @@ void count_launch(int n = 1);
         if (e__ != cudaSuccess)                                                                \
             IDE3D_FAIL(IDE3D_CUDA_ERROR, "%s: %s", #call, cudaGetErrorString(e__));            \
     } while (0)
+
+// Experiment switches (IDE3D_* environment variables) are compiled in only with -DIDE3D_TUNING (IDE3D_BUILD_TUNING=1 python
+// ide-3d_b200/build.py -- what the A/B scripts under scripts/ use).  The product build never reads the environment.
+inline const char* tuning_env(const char* name) {
+#ifdef IDE3D_TUNING
+    return getenv(name);
+#else
+    (void)name;
+    return nullptr;
+#endif
+}
 
 inline int sm_count() {
     static thread_local int cached_dev = -1, cached = 0;

@@ -442,7 +442,7 @@ static bool make_map(const FlFusedArgs& a, CUtensorMap& map) {
     using G = Geom<T, UP, DOWN, FU, FD, CB>;
     memset(&map, 0, sizeof(map));
     if (encode_tiled() == nullptr) return false;
-    if (getenv("IDE3D_FLRELU_NO_TMA") != nullptr) return false;
+    if (tuning_env("IDE3D_FLRELU_NO_TMA") != nullptr) return false;
     if (reinterpret_cast<uintptr_t>(a.x) & 15) return false;
     const CUtensorMapDataType dt = sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const cuuint32_t estr[4] = {1, 1, 1, 1};

@@ -41,6 +41,9 @@ template <int TEAMS> struct Cfg {
 
 struct Args3 {
     TcArgs a;
+    int coop;               // producers: 1 = all eight warps fill one tile together, 0 = two independent teams
+    int stages;             // A buffers in flight (2, or 3 with coop)
+    int prefetch;           // coop producers prefetch the next tile's texel lines into L1
     int sb;                 // index of the sigma block in a.prog.blk
     int nc;                 // number of colour / semantic blocks (the others), cb[] their indices in processing order
     int cb[kTcMaxBlocks];
@@ -72,8 +75,9 @@ __device__ __forceinline__ void softplus16(float (&v)[16], uint32_t bias_addr) {
 
 template <int TEAMS>
 __global__ void __launch_bounds__(Cfg<TEAMS>::kThreads, 1) raymarch_tc3_kernel(const Args3 A) {
-    constexpr int kStages = TEAMS, kTcThreads = Cfg<TEAMS>::kThreads;
+    constexpr int kTcThreads = Cfg<TEAMS>::kThreads;
     const TcArgs& a = A.a;
+    const int kStages = A.stages;
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const TcProgram& P = a.prog;
@@ -128,7 +132,7 @@ __global__ void __launch_bounds__(Cfg<TEAMS>::kThreads, 1) raymarch_tc3_kernel(c
         wsig[tid] = P.blk[A.sb].w2[tid] * 0.6931471805599453f;              // W2_sigma[0][hidden tid] of this 64-unit block
     }
     if (tid == 0) {
-        for (int i = 0; i < kStages; ++i) { tc::mbar_init(&bar_full[i], 4); tc::mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < kStages; ++i) { tc::mbar_init(&bar_full[i], A.coop ? 8 : 4); tc::mbar_init(&bar_empty[i], 1); }
         for (int g = 0; g < kGroups; ++g) {
             tc::mbar_init(&bar_d1s[g], 1); tc::mbar_init(&bar_d1c[g], 1); tc::mbar_init(&bar_d2[g], 1);
             tc::mbar_init(&bar_s2free[g], 4); tc::mbar_init(&bar_d2free[g], 4);
@@ -235,7 +239,8 @@ __global__ void __launch_bounds__(Cfg<TEAMS>::kThreads, 1) raymarch_tc3_kernel(c
         // =========================================================================== producers
         if constexpr (Cfg<TEAMS>::kProducerRegs > Cfg<TEAMS>::kBaseRegs) tc::setmaxnreg_inc<Cfg<TEAMS>::kProducerRegs>();
         else if constexpr (Cfg<TEAMS>::kProducerRegs < Cfg<TEAMS>::kBaseRegs) tc::setmaxnreg_dec<Cfg<TEAMS>::kProducerRegs>();
-        producer_loop<TEAMS>(a, sch, stage_base, bar_full, bar_empty, warp - kFirstProducer, lane);
+        if (A.coop) producer_loop_coop(a, sch, stage_base, bar_full, bar_empty, warp - kFirstProducer, lane, kStages, A.prefetch);
+        else producer_loop<TEAMS>(a, sch, stage_base, bar_full, bar_empty, warp - kFirstProducer, lane);
     } else {
         // =========================================================================== consumers
         if constexpr (Cfg<TEAMS>::kConsumerRegs < Cfg<TEAMS>::kBaseRegs) tc::setmaxnreg_dec<Cfg<TEAMS>::kConsumerRegs>();
@@ -431,7 +436,10 @@ int launch_raymarch_tc3(const TcArgs& a, int teams, cudaStream_t st, bool& handl
     //  IDE3D_TC_TEAMS=3 therefore selects the raymarch_tc.cu kernel)
     handled = (teams == 2) && tc3_eligible(A);
     if (!handled) return IDE3D_OK;
-    const int smem = 2 * a.prog.wpart + teams * kStageBytes + (kTcMaxBlocks * 64 + 64 + 64) * 4 + (2 * kMaxTeams + (6 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
+    A.coop = env_int("IDE3D_TC_COOP", 1, 0, 1);
+    A.stages = A.coop ? env_int("IDE3D_TC_STAGES", 3, 2, 3) : 2;
+    A.prefetch = env_int("IDE3D_TC_PREFETCH", 0, 0, 1);      // measured on B200: 1.34 ms with the prefetch, 1.11 ms without (profiles/r02i_*)
+    const int smem = 2 * a.prog.wpart + A.stages * kStageBytes + (kTcMaxBlocks * 64 + 64 + 64) * 4 + (2 * kMaxTeams + (6 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
     int grid = sm_count();
     if (grid * kGroups > a.num_units) grid = ceil_div(a.num_units, kGroups);
     if (teams == 2) {

@@ -291,6 +291,94 @@ __device__ __forceinline__ void producer_loop(const TcArgs& a, const Schedule& s
     }
 }
 
+// Cooperative variant (raymarch_tc3.cu): ALL eight producer warps fill the same tile -- warp pw takes 16 rows (two pixel columns x 8
+// depth samples of pixel row pw / 2) -- so one tile is in production at a time: half the per-tile latency and half the L1 working
+// set of two independent teams.  `stages` A buffers (2 or 3) are cycled in tile-sequence order; bar_full counts 8 arrivals.
+__device__ __forceinline__ void prefetch_l1(const char* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void producer_loop_coop(const TcArgs& a, const Schedule& sch, unsigned char* stage_base, uint64_t* bar_full,
+                                                   uint64_t* bar_empty, int pw, int lane, int stages, int prefetch) {
+    const int S = a.steps;
+    const int unit_stride = kGroups * gridDim.x;
+    const int total = sch.tiles0 + sch.tiles1;
+    const int shb = (int)(a.tex.sh * 4), swb = (int)(a.tex.sw * 4);
+    const int W = a.tex.w, H = a.tex.h;
+    const int q4 = lane & 7, grp = lane >> 3;
+    const int prow = pw >> 1, half = pw & 1;                                 // pixel row of the unit, which pair of pixel columns
+    const int l16 = lane & 15;                                               // lanes 16..31 mirror 0..15 (same sample)
+    // position (plane grid units) and frame of this lane's sample in tile `seq`
+    auto sample_of = [&](int seq, int& n, float& cx, float& cy, float& cz) {
+        int g, t;
+        if (seq < 2 * sch.m) { g = seq & 1; t = seq >> 1; } else { g = 0; t = sch.m + (seq - 2 * sch.m); }
+        const int ui = t / a.tiles_per_unit, step = t - ui * a.tiles_per_unit;
+        const int unit = blockIdx.x * kGroups + g + ui * unit_stride;
+        const RaySetup r = ray_setup(a, unit, half * 2 + (l16 >> 3), prow);
+        const int s = step * kTileDepth + (l16 & 7);
+        n = r.n;
+        cx = cy = cz = 4.f;                                                   // far outside the planes: every tap gets weight 0
+        if (r.ok && s < S) {
+            const float* M = a.cam2world + r.n * 16;
+            float z0, off0, z1;
+            sample_depths(a, r, s, z0, off0, z1);
+            const float pcx = r.dx * z0 + off0 * r.dx, pcy = r.dy * z0 + off0 * r.dy, pcz = r.dz * z0 + off0 * r.dz;
+            cx = (M[0] * pcx + M[1] * pcy + M[2] * pcz + M[3]) * a.box_scale;
+            cy = (M[4] * pcx + M[5] * pcy + M[6] * pcz + M[7]) * a.box_scale;
+            cz = (M[8] * pcx + M[9] * pcy + M[10] * pcz + M[11]) * a.box_scale;
+        }
+    };
+    int stage = 0, use = 0;
+    for (int seq = 0; seq < total; ++seq) {
+        int n;
+        float cx, cy, cz;
+        sample_of(seq, n, cx, cy, cz);
+        const AxisFoot fx = axis_foot(cx, W), fyr = axis_foot(cy, H), fyc = axis_foot(cy, W), fz = axis_foot(cz, H);
+        const AxisTaps mX = axis_taps(fx.i0, fx.f, W, swb), mYr = axis_taps(fyr.i0, fyr.f, H, shb);
+        const AxisTaps mYc = axis_taps(fyc.i0, fyc.f, W, swb), mZ = axis_taps(fz.i0, fz.f, H, shb);
+        const char* tb = reinterpret_cast<const char*>(a.tex.base + (long long)n * a.tex.sn);
+        const char* sb = reinterpret_cast<const char*>(a.seg.base + (long long)n * a.seg.sn);
+        if (prefetch && seq + 1 < total) {
+            // the NEXT tile's texel lines into L1 while this tile is gathered: each lane owns one sample of it; lanes 0-15 prefetch its
+            // 12 lines of the texture tri-plane, lanes 16-31 the 12 lines of the shape tri-plane (one 128-byte line per tap)
+            int n2;
+            float px, py, pz;
+            sample_of(seq + 1, n2, px, py, pz);
+            const AxisFoot gx = axis_foot(px, W), gyr = axis_foot(py, H), gyc = axis_foot(py, W), gz = axis_foot(pz, H);
+            const AxisTaps pX = axis_taps(gx.i0, gx.f, W, swb), pYr = axis_taps(gyr.i0, gyr.f, H, shb);
+            const AxisTaps pYc = axis_taps(gyc.i0, gyc.f, W, swb), pZ = axis_taps(gz.i0, gz.f, H, shb);
+            const char* pb = reinterpret_cast<const char*>(((lane < 16) ? a.tex.base : a.seg.base) + (long long)n2 * a.tex.sn);
+            prefetch_l1(pb + pYr.lo + pX.lo); prefetch_l1(pb + pYr.lo + pX.hi); prefetch_l1(pb + pYr.hi + pX.lo); prefetch_l1(pb + pYr.hi + pX.hi);
+            prefetch_l1(pb + pZ.lo + pYc.lo + 128); prefetch_l1(pb + pZ.lo + pYc.hi + 128); prefetch_l1(pb + pZ.hi + pYc.lo + 128); prefetch_l1(pb + pZ.hi + pYc.hi + 128);
+            prefetch_l1(pb + pZ.lo + pX.lo + 256); prefetch_l1(pb + pZ.lo + pX.hi + 256); prefetch_l1(pb + pZ.hi + pX.lo + 256); prefetch_l1(pb + pZ.hi + pX.hi + 256);
+        }
+        unsigned char* a_hi = stage_base + stage * kStageBytes;
+        unsigned char* a_lo = a_hi + kTileBytes;
+#pragma unroll 1
+        for (int it = 0; it < 4; ++it) {
+            const int src = it * 4 + grp;                                     // 4 depth-consecutive samples of one ray per instruction
+            AxisTaps X = shfl_taps(mX, src), Yc = shfl_taps(mYc, src);
+            const AxisTaps Yr = shfl_taps(mYr, src), Z = shfl_taps(mZ, src);
+            X.lo += q4 * 16; X.hi += q4 * 16; Yc.lo += q4 * 16; Yc.hi += q4 * 16;
+            const int row = prow * 32 + half * 16 + src;
+            const uint32_t o_tex = tc::sw128_offset(row, q4 >> 1) + (q4 & 1) * 8;
+            const uint32_t o_seg = tc::sw128_offset(row, 4 + (q4 >> 1)) + (q4 & 1) * 8;
+            float f[4], f2[4];
+            uint2 hi, lo;
+            gather24(tb, sb, X, Yr, Yc, Z, f, f2);
+            tc::split4_bf16(f, hi, lo);
+            if (it == 0) tc::mbar_wait(&bar_empty[stage], (use + 1) & 1);     // first use passes immediately
+            *reinterpret_cast<uint2*>(a_hi + o_tex) = hi;
+            *reinterpret_cast<uint2*>(a_lo + o_tex) = lo;
+            tc::split4_bf16(f2, hi, lo);
+            *reinterpret_cast<uint2*>(a_hi + o_seg) = hi;
+            *reinterpret_cast<uint2*>(a_lo + o_seg) = lo;
+        }
+        tc::fence_async_smem();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&bar_full[stage]);
+        if (++stage == stages) { stage = 0; ++use; }
+    }
+}
+
 // Build the hidden-block program from the head list and lay the weight tiles out compactly.  Returns false when the decoder does
 // not fit (hidden not a multiple of 64, more than kTcMaxBlocks blocks, outputs beyond 64 columns).
 inline bool build_program(const ide3d_decoder& d, TcProgram& P) {
@@ -351,8 +439,10 @@ inline bool build_program(const ide3d_decoder& d, TcProgram& P) {
     return true;
 }
 
+// Tuning knobs (IDE3D_TC_*) exist only in a build made with -DIDE3D_TUNING (IDE3D_BUILD_TUNING=1 python ide-3d_b200/build.py), which is
+// what scripts/bench_raymarch.py's A/B runs use; the product build always takes the defaults.
 inline int env_int(const char* name, int dflt, int lo, int hi) {
-    const char* v = getenv(name);
+    const char* v = tuning_env(name);
     if (!v) return dflt;
     const int x = atoi(v);
     return (x < lo || x > hi) ? dflt : x;

@@ -507,7 +507,7 @@ int launch_raymarch_tc_v1(const ide3d_raymarch_params* p, bool channels_last, cu
     a.noise_std = p->noise_std; a.noise = (p->noise_std != 0.f) ? p->noise : nullptr;
     a.out_feat = p->out_feat; a.out_depth = p->out_depth; a.out_weights = p->out_weights;
     a.tiles_x = ceil_div(p->res_w, 2); a.tiles_y = ceil_div(p->res_h, 2);
-    const char* dbg = getenv("IDE3D_TC_DEBUG");
+    const char* dbg = tuning_env("IDE3D_TC_DEBUG");
     a.debug = dbg ? atoi(dbg) : 0;
     IDE3D_CUDA(cudaFuncSetAttribute(raymarch_tc_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     const int num_tiles = a.tiles_x * a.tiles_y * a.n;

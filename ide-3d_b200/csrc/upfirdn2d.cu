@@ -399,7 +399,7 @@ static int launch_patch(const UpfirArgs& p, cudaStream_t st_) {
         // One bulk-tensor copy per tile, double-buffered: both tiles have to fit the 227 KB of one SM.  IDE3D_TMA=0 selects
         // the thread-staged kernel below (kept for tensors the TMA unit cannot describe: unaligned base / row pitch).
         constexpr bool fits = TmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY>::kSmem <= 200 * 1024;
-        const char* tma_env = getenv("IDE3D_TMA");
+        const char* tma_env = tuning_env("IDE3D_TMA");
         if (fits && !(tma_env != nullptr && tma_env[0] == '0') && tma_eligible<T>(p)) {
             const int rc = launch_patch_tma<T, UX, UY, DX, DY, FW, FH, PHX, PHY>(p, st_);
             if (rc != IDE3D_UNSUPPORTED) return rc;
@@ -742,8 +742,8 @@ static int launch_cl_patch(const UpfirArgs& p, cudaStream_t st_) {
     // Measured (scripts/bench_ops.py, [1,512,512,512] fp32): the up=1 FIR runs at 87 % of the HBM peak from TMA tiles (46 % from
     // the L1-gather kernel); 2x upsampling has only 2x2 live taps per output and is faster straight from L1 (85 % vs 80 %).
     if constexpr (UX == 1 && UY == 1 && ClTmaGeom<T, UX, UY, DX, DY, FW, FH, PHX, PHY, 32>::kSmem <= 200 * 1024) {
-        const char* tma_env = getenv("IDE3D_TMA");
-        const char* cb_env = getenv("IDE3D_CL_CB");                         // experiments: force the 32-channel tile shape
+        const char* tma_env = tuning_env("IDE3D_TMA");
+        const char* cb_env = tuning_env("IDE3D_CL_CB");                         // experiments: force the 32-channel tile shape
         const bool ok = !(tma_env != nullptr && tma_env[0] == '0') && encode_tiled() != nullptr && p.in_c % 32 == 0 &&
                         (reinterpret_cast<uintptr_t>(p.x) & 15) == 0 && (p.isw * sizeof(T)) % 16 == 0 && (p.ish * sizeof(T)) % 16 == 0 &&
                         (p.isn * sizeof(T)) % 16 == 0 && p.out_w * (long long)p.out_h >= 64;

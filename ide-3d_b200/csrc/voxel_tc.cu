@@ -244,7 +244,7 @@ int launch_sigma_tc(const ide3d_triplane& seg, const ide3d_decoder& dec, const f
     }
     if (H == nullptr) return IDE3D_OK;
     if (((long long)seg.h * seg.stride_h + (long long)seg.w * seg.stride_w + 96) * 4 >= (1ll << 31)) return IDE3D_OK;
-    if (getenv("IDE3D_VOXEL_SIMT") != nullptr) return IDE3D_OK;
+    if (tuning_env("IDE3D_VOXEL_SIMT") != nullptr) return IDE3D_OK;
     handled = true;
     vtc::Args a;
     a.seg = make_view(seg);

@@ -3,7 +3,8 @@
 delivers them): the round-2 kernel's variants (producer teams, gather instruction shape) and the round-1 kernel, same inputs, plus
 the reference renderer's op chain on the same GPU (tests/test_gpu_speedup.py).  One JSON line per variant.
 
-    python scripts/bench_raymarch.py [--chain]
+    IDE3D_BUILD_TUNING=1 python ide-3d_b200/build.py --force     # the variants are environment switches of a TUNING build
+    python scripts/bench_raymarch.py [--only=<substring of the variant name>]
 """
 import json, os, sys
 import numpy as np
@@ -44,8 +45,9 @@ def main():
 
     base = None
     variants = [('v1 (round 1)', dict(IDE3D_TC_V1='1'))]
-    for teams in ('2',):
-        variants.append((f'v3 teams={teams}', dict(IDE3D_TC_V1='0', IDE3D_TC_V2='0', IDE3D_TC_TEAMS=teams, IDE3D_TC_RAY_MAJOR='1')))
+    for coop, st, pf in (('1', '3', '1'), ('1', '3', '0'), ('1', '2', '1'), ('0', '2', '0')):
+        variants.append((f'v3 coop={coop} stages={st} prefetch={pf}', dict(IDE3D_TC_V1='0', IDE3D_TC_V2='0', IDE3D_TC_TEAMS='2', IDE3D_TC_RAY_MAJOR='1', IDE3D_TC_COOP=coop,
+                                                                            IDE3D_TC_STAGES=st, IDE3D_TC_PREFETCH=pf)))
     for teams in ('2',):
         for rm in ('1',):
             variants.append((f'v2 teams={teams} ray_major={rm}', dict(IDE3D_TC_V1='0', IDE3D_TC_V2='1', IDE3D_TC_TEAMS=teams, IDE3D_TC_RAY_MAJOR=rm)))
@@ -53,7 +55,7 @@ def main():
     for name, env in variants:
         if only and not any(o in name for o in only):
             continue
-        for k in ('IDE3D_TC_V1', 'IDE3D_TC_V2', 'IDE3D_TC_TEAMS', 'IDE3D_TC_RAY_MAJOR'):
+        for k in ('IDE3D_TC_V1', 'IDE3D_TC_V2', 'IDE3D_TC_TEAMS', 'IDE3D_TC_RAY_MAJOR', 'IDE3D_TC_COOP', 'IDE3D_TC_STAGES', 'IDE3D_TC_PREFETCH'):
             os.environ.pop(k, None)
         os.environ.update(env)
         try:
