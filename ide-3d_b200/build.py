@@ -19,7 +19,7 @@ OBJ = os.path.join(HERE, '_build')
 LIBDIR = os.path.join(HERE, 'lib')
 LIB = os.path.join(LIBDIR, 'libide3d_b200.so')
 TUNING = os.environ.get('IDE3D_BUILD_TUNING', '0') == '1'      # experiment switches + the round-1 ray-march kernel (A/B scripts only)
-UNITS = ['capi', 'raymarch', 'raymarch_tc', 'raymarch_tc3'] + (['raymarch_tc_v1'] if TUNING else []) + [ 'voxel', 'voxel_tc', 'stages', 'style_plan', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
+UNITS = ['capi', 'raymarch', 'raymarch_bwd', 'raymarch_tc', 'raymarch_tc3'] + (['raymarch_tc_v1'] if TUNING else []) + [ 'voxel', 'voxel_tc', 'stages', 'style_plan', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
 NVCC_FLAGS = ['-O3', '-std=c++17', '--expt-relaxed-constexpr', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-lineinfo', '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + (['-DIDE3D_TUNING'] if TUNING else [])
 

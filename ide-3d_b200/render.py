@@ -249,3 +249,60 @@ def sigma_grid(planes_tex, planes_seg, decoder, grid_n=256, voxel_origin=(0, 0, 
                                              float(cube_length), float(pre_scale), float(box_scale), int(first),
                                              int(count), L.ptr(out), L.stream_ptr(dev)))
     return out
+
+
+def raymarch_backward(planes_tex, planes_seg, decoder, cam2world, grad_feat, grad_depth, resolution=(64, 64), num_steps=48, fov=18.0,
+                      ray_start=2.25, ray_end=3.3, box_scale=2.0, jitter_u=None, jitter_seed=None, noise=None, noise_std=0.0,
+                      clamp_mode='softplus', last_back=False, white_back=False, max_depth=None, fill_mode=None, z_vals=None,
+                      want_planes=(True, True), want_params=True):
+    """ide3d_raymarch_bwd: gradients of (feat, depth) of `raymarch` w.r.t. the planes and the three decoder heads, one kernel that
+    recomputes the per-sample chain (no materialised intermediates).  -> (d_tex | None, d_seg | None, [dW1, db1, dW2, db2] x 3 | None),
+    or None when the configuration has no backward kernel (the caller then differentiates the composed chain)."""
+    L.require_cuda(planes_tex, planes_seg, cam2world, grad_feat)
+    tex, seg = as_planes(planes_tex), as_planes(planes_seg)
+    dev = tex.device
+    n = tex.shape[0]
+    W, H = (resolution, resolution) if isinstance(resolution, int) else resolution
+    R, S = W * H, int(num_steps if z_vals is None else z_vals.shape[-1])
+    dec = _decoder(decoder, dev)
+    if dec.meta != [(0, 0), (1, N_FEAT), (1, N_FEAT + N_SEG)] or S > 256:
+        return None
+    shapes = [tuple(t.shape) for t in dec.tensors]
+    if shapes != [(64, 32), (64,), (32, 64), (32,), (64, 32), (64,), (19, 64), (19,), (64, 32), (64,), (1, 64), (1,)]:
+        return None
+    cam = cam2world.detach().to(device=dev, dtype=torch.float32).reshape(n, 16).contiguous()
+    p = L.RaymarchParams()
+    p.tex, p.seg, p.dec = L.triplane_view(tex), L.triplane_view(seg), dec.struct
+    p.cam2world = L.ptr(cam)
+    p.n, p.res_w, p.res_h, p.num_steps = n, W, H, S
+    p.fov_deg, p.ray_start, p.ray_end, p.box_scale = float(fov), float(ray_start), float(ray_end), float(box_scale)
+    keep = []
+    if z_vals is not None:
+        zt = z_vals.detach().to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous(); keep.append(zt)
+        p.jitter_mode, p.jitter_u = L.JITTER_ZVALS, L.ptr(zt)
+    elif jitter_u is not None:
+        ju = jitter_u.detach().to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous(); keep.append(ju)
+        p.jitter_mode, p.jitter_u = L.JITTER_TENSOR, L.ptr(ju)
+    elif jitter_seed is not None:
+        p.jitter_mode, p.jitter_seed = L.JITTER_HASH, int(jitter_seed) & 0xFFFFFFFFFFFFFFFF
+    else:
+        p.jitter_mode = L.JITTER_NONE
+    if noise is not None and noise_std:
+        nz = noise.detach().to(device=dev, dtype=torch.float32).reshape(n, R, S).contiguous(); keep.append(nz)
+        p.noise, p.noise_std = L.ptr(nz), float(noise_std)
+    p.clamp_mode = L.CLAMP_SOFTPLUS if clamp_mode == 'softplus' else L.CLAMP_RELU
+    p.last_back, p.white_back = int(bool(last_back)), int(bool(white_back))
+    p.max_depth, p.fill_weight = float(max_depth or 0.0), int(fill_mode == 'weight')
+    gf = grad_feat.detach().to(device=dev, dtype=torch.float32).reshape(n, R, N_OUT - 1).contiguous()
+    gd = None if grad_depth is None else grad_depth.detach().to(device=dev, dtype=torch.float32).reshape(n, R).contiguous()
+    d_tex = torch.zeros_like(tex) if want_planes[0] else None               # channels-last, like the forward's planes
+    d_seg = torch.zeros_like(seg) if want_planes[1] else None
+    d_par = [torch.zeros(sh, dtype=torch.float32, device=dev) for sh in shapes] if want_params else None
+    ptrs = None
+    if d_par is not None:
+        ptrs = (C.c_void_p * 12)(*[t.data_ptr() for t in d_par])
+    with torch.cuda.device(dev):
+        rc = L.get_lib().ide3d_raymarch_bwd(C.byref(p), L.ptr(gf), L.ptr(gd), L.ptr(d_tex), L.ptr(d_seg), ptrs, L.stream_ptr(dev))
+    if L.check(rc, allow_unsupported=True) == L.UNSUPPORTED:
+        return None
+    return d_tex, d_seg, d_par

@@ -16,6 +16,7 @@ import torch
 import torch.nn.functional as F
 
 N_FEAT, N_OUT = 32, 52
+USE_BACKWARD_KERNEL = True    # ide3d_raymarch_bwd for the planes / decoder gradients; False = always differentiate the composed chain
 RAYS_PER_SLAB = 1024          # rays per recompute slab: bounds the materialised [n, rays, S, 52+64+...] tensors
 
 
@@ -130,6 +131,21 @@ class RaymarchFunction(torch.autograd.Function):
         tex, seg, cam2world, jitter_u, noise, *params = ctx.saved_tensors
         cfg = ctx.cfg
         need = ctx.needs_input_grad[6:]
+        # fast path: the backward kernel (ide3d_raymarch_bwd) -- planes + three-head decoder, no camera / per-sample-weight gradients
+        want_w = ctx.want_weights and dweights is not None and dweights.ndim == 4 and bool((dweights != 0).any())
+        if USE_BACKWARD_KERNEL and tex.is_cuda and not need[2] and not want_w:
+            from . import render
+            heads = [(m[0], m[1]) + tuple(params[4 * i:4 * i + 4]) for i, m in enumerate(ctx.head_meta)]
+            kw = dict(resolution=(cfg['W'], cfg['H']), num_steps=cfg['S'], fov=cfg['fov'], ray_start=cfg['ray_start'], ray_end=cfg['ray_end'],
+                      box_scale=cfg['box_scale'], jitter_u=jitter_u, jitter_seed=cfg.get('jitter_seed'), noise=noise, noise_std=cfg.get('noise_std', 0.0),
+                      clamp_mode=cfg['clamp_mode'], last_back=cfg['last_back'], white_back=cfg['white_back'], max_depth=cfg['max_depth'],
+                      fill_mode='weight' if cfg['fill_weight'] else None)
+            res = render.raymarch_backward(tex, seg, heads, cam2world, dfeat, ddepth, want_planes=(bool(need[0]), bool(need[1])),
+                                           want_params=any(need[3:]), **kw)
+            if res is not None:
+                d_tex, d_seg, d_par = res
+                gp = [None] * len(params) if d_par is None else [g.reshape(p.shape).to(p.dtype) if nd else None for g, p, nd in zip(d_par, params, need[3:])]
+                return (None, None, None, None, None, None, d_tex if need[0] else None, d_seg if need[1] else None, None) + tuple(gp)
         leaves = [t.detach().requires_grad_(bool(nd)) for t, nd in zip((tex, seg, cam2world) + tuple(params), need)]
         wanted = [t for t in leaves if t.requires_grad]
         grads = [torch.zeros_like(t) for t in wanted]

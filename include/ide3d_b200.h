@@ -241,6 +241,15 @@ typedef struct ide3d_raymarch_params {
 } ide3d_raymarch_params;
 int ide3d_raymarch_fwd(const ide3d_raymarch_params* p, ide3d_stream_t stream);
 
+/* Backward of ide3d_raymarch_fwd: what autograd derives in the reference from grid_sample (grid_sample_gradfix.py:55-61), the decoder
+ * layers and fancy_integration (volumetric_rendering.py:34-74), in one kernel that recomputes the per-sample chain instead of storing it.
+ * p: the forward's parameters (outputs ignored).  grad_feat [N,R,51], grad_depth [N,R] or NULL.  grad_tex / grad_seg: fp32 buffers with
+ * the planes' (channels-last) strides, ZERO-INITIALISED by the caller, accumulated into with red.global.add; either may be NULL.
+ * grad_params: NULL, or 12 pointers {dW1, db1, dW2, db2} x 3 heads (dense, the heads' shapes), zero-initialised, accumulated into.
+ * No gradient for cam2world / jitter / noise.  IDE3D_UNSUPPORTED for decoders other than the three-head one, NCHW planes, > 256 samples. */
+int ide3d_raymarch_bwd(const ide3d_raymarch_params* p, const float* grad_feat, const float* grad_depth, float* grad_tex,
+                       float* grad_seg, float* const* grad_params, ide3d_stream_t stream);
+
 /* sample_voxel: decode `points` [N, P, 3] (world units) -> out [N, P, 52], or, with sigma_only,
  * out [N, P] holding channel 51 only. */
 int ide3d_sample_voxel(const ide3d_triplane* tex, const ide3d_triplane* seg, const ide3d_decoder* dec,

@@ -95,3 +95,54 @@ def test_generator_synthesis_is_differentiable_end_to_end():
     r = G.synthesis.renderer
     assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in r.parameters())
     assert r.sigma_net.fc2.weight.grad.abs().max() > 0 and G.synthesis.vb32.conv1.weight.grad.abs().max() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('opts', [dict(), dict(white_back=True, max_depth=3.3, last_back=True), dict(clamp_mode='relu'), dict(fill_mode='weight')])
+@pytest.mark.parametrize('jitter', ['tensor', 'hash'])
+def test_backward_kernel_matches_oracle_autograd(opts, jitter):
+    """ide3d_raymarch_bwd (one kernel: recompute + compositing adjoint + decoder adjoint + red.add scatter) against autograd through the
+    oracle's restatement of the reference functions: plane gradients and all twelve decoder-head gradients.  The camera takes no
+    gradient here (that request keeps the composed-chain path, covered above)."""
+    from ide3d_b200 import render, render_grad
+    tex, seg, dec, cam = _random_case(2, 16, seed=4)
+    g = torch.Generator().manual_seed(1)
+    u = torch.rand(2, RES[0] * RES[1], S, 1, generator=g) if jitter == 'tensor' else None
+    seed = None if jitter == 'tensor' else 0x1234_5678_9ABC_DEF1
+    gf, gd = torch.randn(2, 30, 51, generator=g), torch.randn(2, 30, 1, generator=g)
+    u_ref = u if u is not None else torch.from_numpy(orr.hash_uniform(torch.arange(2 * 30 * S).numpy(), seed)).reshape(2, 30, S, 1)
+    rgb, depth, gt, gs, _, gp = _oracle_grads(tex, seg, dec, cam, u_ref, gf, gd, **opts)
+
+    dev = 'cuda'
+    heads = [tuple(h[:2]) + tuple(t.to(dev).requires_grad_(True) for t in h[2:]) for h in three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)]
+    t, s = [x.to(dev).requires_grad_(True) for x in (tex, seg)]
+    calls = []
+    orig = render.raymarch_backward
+    render.raymarch_backward = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    try:
+        feat, d, _ = render.raymarch(t, s, heads, cam.to(dev), resolution=RES, num_steps=S, jitter_u=None if u is None else u.to(dev), jitter_seed=seed, **opts)
+        (feat * gf.to(dev)).sum().add((d * gd.to(dev)).sum()).backward()
+    finally:
+        render.raymarch_backward = orig
+    assert calls, 'the backward kernel path was not taken'
+    tol = lambda ref: 5e-4 * max(1.0, ref.abs().max().item())
+    assert (t.grad.cpu() - gt).abs().max() <= tol(gt), 'tex'
+    assert (s.grad.cpu() - gs).abs().max() <= tol(gs), 'seg'
+    H = 64
+    w1g, b1g, w2g, b2g = gp
+    blocks = [(slice(0, H), slice(0, 32), slice(0, 32)), (slice(H, 2 * H), slice(32, 64), slice(32, 51)), (slice(2 * H, 3 * H), slice(32, 64), slice(51, 52))]
+    for (in_sel, off, hw1, hb1, hw2, hb2), (hs, ks, os_) in zip(heads, blocks):
+        assert (hw1.grad.cpu() - w1g[hs, ks]).abs().max() <= tol(w1g), 'w1'
+        assert (hb1.grad.cpu() - b1g[hs]).abs().max() <= tol(b1g), 'b1'
+        assert (hw2.grad.cpu() - w2g[os_, hs]).abs().max() <= tol(w2g), 'w2'
+        assert (hb2.grad.cpu() - b2g[os_]).abs().max() <= tol(b2g), 'b2'
+    # and the kernel agrees with the composed-chain backward it replaces
+    render_grad.USE_BACKWARD_KERNEL = False
+    try:
+        t2, s2 = [x.to(dev).requires_grad_(True) for x in (tex, seg)]
+        heads2 = [tuple(h[:2]) + tuple(x.detach().clone().requires_grad_(True) for x in h[2:]) for h in heads]
+        feat2, d2, _ = render.raymarch(t2, s2, heads2, cam.to(dev), resolution=RES, num_steps=S, jitter_u=None if u is None else u.to(dev), jitter_seed=seed, **opts)
+        (feat2 * gf.to(dev)).sum().add((d2 * gd.to(dev)).sum()).backward()
+    finally:
+        render_grad.USE_BACKWARD_KERNEL = True
+    assert (t.grad - t2.grad).abs().max() <= tol(gt) and (heads[2][2].grad - heads2[2][2].grad).abs().max() <= tol(w1g)
