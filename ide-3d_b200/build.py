@@ -15,11 +15,11 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
-OBJ = os.path.join(HERE, '_build')
+OBJ = os.path.join(HERE, '_build_tuning' if os.environ.get('IDE3D_BUILD_TUNING', '0') == '1' else '_build')
 LIBDIR = os.path.join(HERE, 'lib')
-LIB = os.path.join(LIBDIR, 'libide3d_b200.so')
+LIB = os.path.join(LIBDIR, 'libide3d_b200_tuning.so' if os.environ.get('IDE3D_BUILD_TUNING', '0') == '1' else 'libide3d_b200.so')
 TUNING = os.environ.get('IDE3D_BUILD_TUNING', '0') == '1'      # experiment switches + the round-1 ray-march kernel (A/B scripts only)
-UNITS = ['capi', 'raymarch', 'raymarch_bwd', 'raymarch_tc', 'raymarch_tc3'] + (['raymarch_tc_v1'] if TUNING else []) + [ 'voxel', 'voxel_tc', 'stages', 'style_plan', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
+UNITS = ['capi', 'raymarch', 'raymarch_bwd', 'raymarch_tc', 'raymarch_tc3'] + (['raymarch_tc_v1'] if TUNING else []) + [ 'voxel', 'voxel_tc', 'stages', 'style_plan', 'mcubes', 'bias_act', 'upfirdn2d', 'filtered_lrelu', 'filtered_lrelu_fused']
 NVCC_FLAGS = ['-O3', '-std=c++17', '--expt-relaxed-constexpr', '-gencode', 'arch=compute_100a,code=sm_100a',
               '-lineinfo', '-Xcompiler', '-fPIC', '-Xptxas', '-v'] + (['-DIDE3D_TUNING'] if TUNING else [])
 
@@ -64,7 +64,7 @@ def build(force=False, verbose=False):
     """Compile if the sources changed since the last build; return the library path."""
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
-    stamp = os.path.join(LIBDIR, 'build.sha256')
+    stamp = os.path.join(LIBDIR, 'build_tuning.sha256' if TUNING else 'build.sha256')
     digest = _digest()
     if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
         return LIB

@@ -1,0 +1,141 @@
+"""Marching cubes on the GPU: the step that follows extract_shapes' sigma grid (render_mesh.py:30-32,
+`vertices, triangles = mcubes.marching_cubes(voxel_grid, sigma_threshold)`; dnnlib/geometry.py:282-286 calls it the same way).
+
+PyMCubes (environment.yml:29, unpinned) is a third-party dependency that is not part of the reference tree, so this is a restatement of
+the published algorithm (Lorensen & Cline 1987), not of PyMCubes' source: cell configuration from the 8 corner signs, triangles from a
+256-entry table, vertices by linear interpolation along the cut edges, one indexed mesh (vertices shared between cells).  The table is
+GENERATED here from first principles (`build_tables`) rather than typed in: per configuration the cut edges are linked into closed loops
+face by face and fan-triangulated; the ambiguous faces (two diagonal inside corners) always separate the inside corners, the same rule
+for both cells that share the face, which makes the surface watertight.  The generated table has the classic shape (820 triangles over
+the 256 configurations, at most 5 per cell).  Conventions follow PyMCubes: volume indexed [x, y, z], vertices in index units, a corner is
+inside where value >= threshold... the orientation / inside test of PyMCubes itself is not recoverable here (parity unpinned; the tests
+pin the geometry instead: watertightness, Euler characteristic, vertices on the iso-level, area / volume of analytic shapes).
+
+    vertices, triangles = marching_cubes(volume, threshold)      # volume: CUDA tensor [nx, ny, nz] (any float dtype)
+"""
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib as L
+
+
+def build_tables():
+    """-> tri [256,16] int8 (edge triples, -1 terminated), ntri [256] int32, edge_corner [12,2] int32.
+    corner i = (i & 1, i >> 1 & 1, i >> 2 & 1); edge e = axis * 4 + k joins corner c0 (bit `axis` clear, k-th such corner) and c0 | 1 << axis."""
+    corners = np.array([[i & 1, (i >> 1) & 1, (i >> 2) & 1] for i in range(8)])
+    edge_corner = [(c0, c0 | (1 << a)) for a in range(3) for c0 in range(8) if not (c0 >> a) & 1]
+    edge_of = {frozenset(ec): e for e, ec in enumerate(edge_corner)}
+    faces = []
+    for a in range(3):
+        b, c = [(1, 2), (0, 2), (0, 1)][a]
+        for val in (0, 1):
+            cyc = []
+            for vb, vc in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                p = [0, 0, 0]
+                p[a], p[b], p[c] = val, vb, vc
+                cyc.append(p[0] | (p[1] << 1) | (p[2] << 2))
+            faces.append(cyc)
+    tri = -np.ones((256, 16), np.int8)
+    ntri = np.zeros(256, np.int32)
+    for cfg in range(256):
+        inside = [(cfg >> i) & 1 for i in range(8)]
+        adj = {}
+        for cyc in faces:
+            fl = [inside[c] for c in cyc]
+            fe = [edge_of[frozenset((cyc[k], cyc[(k + 1) % 4]))] for k in range(4)]
+            cross = [k for k in range(4) if fl[k] != fl[(k + 1) % 4]]
+            pairs = []
+            if len(cross) == 2:
+                pairs = [(fe[cross[0]], fe[cross[1]])]
+            elif len(cross) == 4:                                   # ambiguous face: cut off each inside corner on its own
+                pairs = [(fe[(k - 1) % 4], fe[k]) for k in range(4) if fl[k]]
+            for e1, e2 in pairs:
+                adj.setdefault(e1, []).append(e2)
+                adj.setdefault(e2, []).append(e1)
+        seen, out = set(), []
+        for e0 in sorted(adj):
+            if e0 in seen:
+                continue
+            loop, prev, cur = [e0], None, e0
+            seen.add(e0)
+            while True:
+                n = adj[cur][0] if prev is None else [x for x in adj[cur] if x != prev][0]
+                if n == e0:
+                    break
+                loop.append(n)
+                seen.add(n)
+                prev, cur = cur, n
+            # orientation: the loop normal points from the inside corners to the outside ones
+            mid = np.array([(corners[edge_corner[e][0]] + corners[edge_corner[e][1]]) / 2.0 for e in loop])
+            g = np.zeros(3)
+            for e in loop:
+                c0, c1 = edge_corner[e]
+                g += (corners[c1] - corners[c0]) * (1 if inside[c0] else -1)
+            nrm = sum(np.cross(mid[i], mid[(i + 1) % len(loop)]) for i in range(len(loop)))
+            if np.dot(nrm, g) < 0:
+                loop = loop[::-1]
+            for i in range(1, len(loop) - 1):
+                out += [loop[0], loop[i], loop[i + 1]]
+        assert len(out) <= 15
+        tri[cfg, :len(out)] = out
+        ntri[cfg] = len(out) // 3
+    return tri, ntri, np.array(edge_corner, np.int32)
+
+
+_tables = {}
+
+
+def _device_tables(device):
+    key = str(device)
+    if key not in _tables:
+        tri, ntri, ec = build_tables()
+        _tables[key] = (torch.from_numpy(tri).to(device), torch.from_numpy(ntri).to(device), torch.from_numpy(ec).to(device).contiguous())
+    return _tables[key]
+
+
+@torch.no_grad()
+def marching_cubes(volume, threshold):
+    """volume [nx, ny, nz] on a CUDA device -> (vertices [V, 3] float32 in index units (x, y, z), triangles [T, 3] int64).
+    Inside = value >= threshold; triangle normals point from inside to outside.  Vertices are shared between the cells that cut the same
+    grid edge (de-duplicated exactly by edge id) and ordered by that id; triangles are ordered by cell."""
+    L.require_cuda(volume)
+    if volume.ndim != 3:
+        raise ValueError('marching_cubes: volume must be a 3-D array')
+    v = volume.detach().to(torch.float32).contiguous()
+    nx, ny, nz = v.shape
+    if min(nx, ny, nz) < 2:
+        raise ValueError('marching_cubes: the grid needs at least 2 points per axis')
+    dev = v.device
+    tri, ntri, ec = _device_tables(dev)
+    cells = (nx - 1) * (ny - 1) * (nz - 1)
+    counts = torch.empty(cells, dtype=torch.uint8, device=dev)
+    lib = L.get_lib()
+    with torch.cuda.device(dev):
+        L.check(lib.ide3d_mc_classify(L.ptr(v), nx, ny, nz, float(threshold), L.ptr(ntri), L.ptr(counts), L.stream_ptr(dev)))
+        offsets = torch.cumsum(counts, 0, dtype=torch.int64)                       # the one library call: an inclusive scan
+        total = int(offsets[-1].item()) if cells else 0
+        if total == 0:
+            return torch.zeros(0, 3, device=dev), torch.zeros(0, 3, dtype=torch.int64, device=dev)
+        edge_ids = torch.empty(total * 3, dtype=torch.int64, device=dev)
+        verts = torch.empty(total * 3, 3, dtype=torch.float32, device=dev)
+        L.check(lib.ide3d_mc_emit(L.ptr(v), nx, ny, nz, float(threshold), L.ptr(tri), L.ptr(ec), L.ptr(counts), L.ptr(offsets),
+                                  L.ptr(edge_ids), L.ptr(verts), L.stream_ptr(dev)))
+    uniq, inverse = torch.unique(edge_ids, return_inverse=True)                     # vertex = cut grid edge
+    vertices = torch.empty(uniq.numel(), 3, dtype=torch.float32, device=dev)
+    vertices[inverse] = verts                                                       # duplicates are bit-identical by construction
+    return vertices, inverse.reshape(total, 3)
+
+
+@torch.no_grad()
+def mesh_from_sigma_grid(sigma, size=None, sigma_threshold=10.0):
+    """render_mesh.py:29-32 on the device: clamp the density grid at 0, marching cubes at `sigma_threshold`, vertices scaled by 1/size.
+    sigma: [n, n, n] (or flat n^3, the layout extract_shapes.py writes) CUDA tensor.  -> (vertices [V,3] in [0,1), triangles [T,3])."""
+    if sigma.ndim == 1:
+        n = round(sigma.numel() ** (1 / 3))
+        sigma = sigma.reshape(n, n, n)
+    size = sigma.shape[0] if size is None else size
+    vertices, triangles = marching_cubes(torch.clamp_min(sigma, 0), sigma_threshold)
+    return vertices / float(size), triangles

@@ -303,6 +303,18 @@ int ide3d_sample_pdf(const float* bins, const float* weights, const float* u, in
 int ide3d_mask2color(const float* masks, int n, int c, int h, int w, int64_t stride_n, int64_t stride_c, int64_t stride_h,
                      int64_t stride_w, const float* lut, void* out, int out_u8, ide3d_stream_t stream);
 
+/* Marching cubes on a density grid (render_mesh.py:30-32 / dnnlib/geometry.py:282-286 call PyMCubes' marching_cubes on the host).
+ * volume [nx, ny, nz] fp32 dense (index (x*ny + y)*nz + z); a corner is inside where value >= threshold.  Tables (device memory) come
+ * from ide3d_b200/mesh.py::build_tables: ntri_table [256] int32, tri_table [256*16] int8 (edge triples, -1 terminated), edge_corner
+ * [12*2] int32 (lower / upper corner of each cube edge).
+ *   ide3d_mc_classify: counts[cell] = number of triangles of the cell, cell = (x*(ny-1) + y)*(nz-1) + z.
+ *   ide3d_mc_emit:     offsets = inclusive scan of counts (int64); per emitted vertex k of triangle t: edge_ids[3t+k] = global id of the
+ *                      cut grid edge ((lower corner flat index)*3 + axis), verts[(3t+k)*3 ..] = its position in index units. */
+int ide3d_mc_classify(const float* volume, int nx, int ny, int nz, float threshold, const int* ntri_table, unsigned char* counts,
+                      ide3d_stream_t stream);
+int ide3d_mc_emit(const float* volume, int nx, int ny, int nz, float threshold, const signed char* tri_table, const int* edge_corner,
+                  const unsigned char* counts, const int64_t* offsets, int64_t* edge_ids, float* verts, ide3d_stream_t stream);
+
 /* Style vectors and demodulation coefficients of every modulated convolution of one synthesis call, two launches
  * (replaces per layer: FullyConnectedLayer.forward of the affine, inversion/networks.py:136-165 / :476, and the dcoefs
  * reduction of modulated_conv2d, :89-90).

@@ -183,3 +183,38 @@ def test_render_interp_video_batched_driver(G):
     assert grids.dtype == torch.uint8 and tuple(grids.shape) == (4, 64, 128, 3) and (F, gh, gw) == (4, 1, 2)
     want = (one[0] * 127.5 + 128).clamp(0, 255).to(torch.uint8).permute(1, 2, 0)
     assert (grids[1, :, :64].int() - want.int()).abs().max() <= 1
+
+
+def test_conv2d_gradfix_gradient_penalty():
+    """conv2d_gradfix (torch_utils/ops/conv2d_gradfix.py:66-198): gradients of gradients (R1 / path-length penalties) and the
+    no_weight_gradients() switch.  For y = conv(x, w): d/dx sum(y * r) = conv_transpose(r, w), so the penalty P = |dL/dx|^2 is an explicit
+    function of w; its autograd gradient through the module must equal the gradient of that explicit form."""
+    from ide3d_b200.torch_utils.ops import conv2d_gradfix as cg
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 3, 9, 9, generator=g, dtype=torch.float64, requires_grad=True)
+    w = torch.randn(4, 3, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    r = torch.randn(2, 4, 9, 9, generator=g, dtype=torch.float64)
+    y = cg.conv2d(x, w, padding=1)
+    (gx,) = torch.autograd.grad((y * r).sum(), x, create_graph=True)
+    gx.square().sum().backward()
+    w2 = w.detach().clone().requires_grad_(True)
+    torch.nn.functional.conv_transpose2d(r, w2, padding=1).square().sum().backward()
+    assert torch.allclose(w.grad, w2.grad, rtol=1e-10, atol=1e-10)
+    # transposed convolution: same statement with the roles swapped
+    wt = torch.randn(3, 4, 3, 3, generator=g, dtype=torch.float64, requires_grad=True)
+    yt = cg.conv_transpose2d(x, wt, stride=2, padding=1)
+    rt = torch.randn(*yt.shape, generator=g, dtype=torch.float64)
+    (gxt,) = torch.autograd.grad((yt * rt).sum(), x, create_graph=True)
+    gxt.square().sum().backward()
+    wt2 = wt.detach().clone().requires_grad_(True)
+    torch.nn.functional.conv2d(rt, wt2, stride=2, padding=1).square().sum().backward()
+    assert torch.allclose(wt.grad, wt2.grad, rtol=1e-10, atol=1e-10)
+    # no_weight_gradients(): the input gradient is unchanged, the weight receives nothing (first and second order)
+    w3 = w.detach().clone().requires_grad_(True)
+    x3 = x.detach().clone().requires_grad_(True)
+    with cg.no_weight_gradients():
+        y3 = cg.conv2d(x3, w3, padding=1)
+        (gx3,) = torch.autograd.grad((y3 * r).sum(), x3, create_graph=True)
+    assert torch.allclose(gx3, gx.detach()) and w3.grad is None
+    assert torch.autograd.grad(gx3.square().sum(), [w3, x3], allow_unused=True)[0] is None      # nothing reaches the weight, at any order
+    assert cg.weight_gradients_disabled is False
