@@ -362,13 +362,13 @@ def main():
             'e2e': {'value': e2e_value, 'unit': 'frames/s', 'h2d_bytes_per_step': int((ws_pin.numel() * 4 + c_pin.numel() * 4) // args.steps),
                     'd2h_bytes_per_step': int(BATCH * world * 3 * 512 * 512), 'call': 'ide3d_b200.dist.stream_frames_sharded (pinned host ws/c -> uint8 frames in pinned host memory; D2H of batch i overlaps batch i+1)'},
             'gpu_launches': int(launches),
-            'roofline': {'kernel': 'raymarch_tc_kernel (fused gather + tcgen05 decoder MLP + compositing)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'kernel': 'tc3::raymarch_tc3_kernel (fused gather + tcgen05 decoder MLP, compositing folded into the layer-2 operand)', 'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': peak_src, 'kernel_ms': kern_ms,
                          'algorithmic_bytes_per_launch': BATCH * FRAME_ALGO_BYTES,
                          'kernel_only_fps': BATCH / (kern_ms * 1e-3), 'renderer_fps_incl_layout_pass': BATCH / (renderer_ms * 1e-3),
                          'reference_gpu_chain_ms': chain_ms, 'vs_reference_gpu_chain': chain_ms / kern_ms,
                          'vs_reference_gpu_chain_note': 'reference renderer op chain (rays, jitter, bmm, 6x grid_sample, decoder matmuls, compositing; every stage in HBM) on this GPU, same planes and decoder, / kernel_ms; north-star target >= 20',
-                         'note': 'HBM is not the limiter of this kernel: 24 texel lines per sample are served by L1/L2 and the kernel is issue/XU bound (profiles/r01_ncu_raymarch_tc_v2.txt); frac is reported as the contract asks'},
+                         'note': 'HBM is not the limiter of this kernel: 24 texel lines per sample are served by L1/L2 and the kernel is gather-latency bound (profiles/r02k_ncu_raymarch_tc3.txt); frac is reported as the contract asks'},
             'clocks': clocks.summary(),
         }
         if not args.no_cpu_baseline and world == 1:
