@@ -442,13 +442,8 @@ int launch_raymarch_tc3(const TcArgs& a, int teams, cudaStream_t st, bool& handl
     const int smem = 2 * a.prog.wpart + A.stages * kStageBytes + (kTcMaxBlocks * 64 + 64 + 64) * 4 + (2 * kMaxTeams + (6 + kTcMaxBlocks) * kGroups) * 8 + 16 + 1024;
     int grid = sm_count();
     if (grid * kGroups > a.num_units) grid = ceil_div(a.num_units, kGroups);
-    if (teams == 2) {
-        IDE3D_CUDA(cudaFuncSetAttribute(tc3::raymarch_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        tc3::raymarch_tc3_kernel<2><<<grid, tc3::Cfg<2>::kThreads, smem, st>>>(A);
-    } else {
-        IDE3D_CUDA(cudaFuncSetAttribute(tc3::raymarch_tc3_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        tc3::raymarch_tc3_kernel<3><<<grid, tc3::Cfg<3>::kThreads, smem, st>>>(A);
-    }
+    IDE3D_CUDA(cudaFuncSetAttribute(tc3::raymarch_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    tc3::raymarch_tc3_kernel<2><<<grid, tc3::Cfg<2>::kThreads, smem, st>>>(A);
     IDE3D_CHECK_LAUNCH("raymarch_tc3_kernel");
     return IDE3D_OK;
 }
