@@ -480,6 +480,25 @@ __device__ __forceinline__ void cl_patch_body(const UpfirArgs& p, const float (&
         for (int b = 0; b < kPatch; ++b)
 #pragma unroll
             for (int c = 0; c < 4; ++c) acc[a][b][c] = 0.f;
+    if (p.add != nullptr) {
+        // skip-connection form (upsample2d(img) + y + b): the accumulators START from the new contribution, so its 16 loads are in
+        // flight together with the window loads instead of after the FIR (the kernel is latency bound: long-scoreboard 11.7 per issue at
+        // 46 % of the HBM peak, profiles/r02p_ncu_step_fir_epilogue_kernels.txt) -- same registers, twice the loads in flight
+        const T* ain = (const T*)p.add + n * p.asn + cv * 4;
+        float bv[4] = {0.f, 0.f, 0.f, 0.f};
+        if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
+#pragma unroll
+        for (int a = 0; a < kPatch; ++a) {
+#pragma unroll
+            for (int b = 0; b < kPatch; ++b)
+                if (oy0 + a < p.out_h && ox0 + b < p.out_w) {
+                    float av[4];
+                    V4<T>::ld(ain + (oy0 + a) * p.ash + (ox0 + b) * p.asw, av);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[a][b][c] = av[c] + bv[c];
+                }
+        }
+    }
 
 #pragma unroll
     for (int r = 0; r < AY::kWin; ++r) {
@@ -504,23 +523,6 @@ __device__ __forceinline__ void cl_patch_body(const UpfirArgs& p, const float (&
         }
     }
     T* yout = (T*)p.y + n * p.osn + cv * 4;
-    if (p.add != nullptr) {                                  // skip-connection form: + new contribution (+ its bias)
-        const T* ain = (const T*)p.add + n * p.asn + cv * 4;
-        float bv[4] = {0.f, 0.f, 0.f, 0.f};
-        if (p.bias != nullptr) V4<T>::ld((const T*)p.bias + cv * 4, bv);
-#pragma unroll
-        for (int a = 0; a < kPatch; ++a) {
-            if (oy0 + a >= p.out_h) break;
-#pragma unroll
-            for (int b = 0; b < kPatch; ++b)
-                if (ox0 + b < p.out_w) {
-                    float av[4];
-                    V4<T>::ld(ain + (oy0 + a) * p.ash + (ox0 + b) * p.asw, av);
-#pragma unroll
-                    for (int c = 0; c < 4; ++c) acc[a][b][c] += av[c] + bv[c];
-                }
-        }
-    }
     if constexpr (kEpi) {
         float dv[4] = {1.f, 1.f, 1.f, 1.f}, bv[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {1.f, 1.f, 1.f, 1.f};
         if (p.scale != nullptr) V4<T>::ld((const T*)p.scale + (long long)n * p.in_c + cv * 4, dv);
