@@ -384,6 +384,24 @@ class SegSynthesisBlock(SynthesisBlock):
         super().__init__(in_channels, out_channels, w_dim, resolution, img_channels + seg_channels, is_last, **kwargs)
         self.img_channels, self.seg_channels = img_channels, seg_channels
 
+    def _load_from_state_dict(self, state_dict, prefix, *args, **kwargs):
+        """Checkpoints of the in-repo reference class (inversion/networks.py:1093-1134) carry two output layers, `torgb` and `toseg`,
+        each with its own affine.  They are the same function as this block's single [img | seg] ToRGB exactly when the two affines
+        coincide; then the weights / biases are concatenated along the output channels.  Anything else cannot be represented by the
+        released 3-children-per-block structure this class follows, and fails loudly instead of loading half a block."""
+        ts = prefix + 'toseg.'
+        if any(k.startswith(ts) for k in state_dict):
+            for name in ('affine.weight', 'affine.bias'):
+                a, b = state_dict.get(prefix + 'torgb.' + name), state_dict.get(ts + name)
+                if a is None or b is None or a.shape != b.shape or not torch.equal(a, b):
+                    raise RuntimeError(f'SegSynthesisBlock: {ts}{name} differs from torgb.{name}; a block with independent torgb / toseg '
+                                       'affines has no equivalent in this single-ToRGB structure')
+            for name in ('weight', 'bias'):
+                state_dict[prefix + 'torgb.' + name] = torch.cat([state_dict[prefix + 'torgb.' + name], state_dict[ts + name]], 0)
+            for k in [k for k in state_dict if k.startswith(ts)]:
+                del state_dict[k]
+        return super()._load_from_state_dict(state_dict, prefix, *args, **kwargs)
+
     def forward(self, x, img, ws, condition_img=None, force_fp32=False, fused_modconv=None, **layer_kwargs):
         x, w_shared, fused_modconv, rgb_in = self._features(x, ws, force_fp32, fused_modconv, layer_kwargs)
         if self._fuse_skip(rgb_in, img, condition_img):

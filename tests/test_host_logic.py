@@ -218,3 +218,25 @@ def test_conv2d_gradfix_gradient_penalty():
     assert torch.allclose(gx3, gx.detach()) and w3.grad is None
     assert torch.autograd.grad(gx3.square().sum(), [w3, x3], allow_unused=True)[0] is None      # nothing reaches the weight, at any order
     assert cg.weight_gradients_disabled is False
+
+
+def test_seg_block_loads_reference_style_torgb_toseg_state_dict():
+    """a state_dict with separate torgb / toseg layers (the in-repo reference class, inversion/networks.py:1093-1134) is
+    merged into the block's single [img | seg] ToRGB when the two affines are tied, and refused loudly when they are not."""
+    from ide3d_b200.training.networks import SegSynthesisBlock
+    torch.manual_seed(0)
+    blk = SegSynthesisBlock(8, 8, w_dim=16, resolution=8, img_channels=6, seg_channels=6, is_last=False)
+    sd = blk.state_dict()
+    w, b = sd.pop('torgb.weight'), sd.pop('torgb.bias')
+    ref = dict(sd)
+    ref['torgb.weight'], ref['torgb.bias'] = w[:6].clone(), b[:6].clone() + 0.5
+    ref['toseg.weight'], ref['toseg.bias'] = w[6:].clone() * 2, b[6:].clone() - 0.5
+    ref['toseg.affine.weight'], ref['toseg.affine.bias'] = sd['torgb.affine.weight'].clone(), sd['torgb.affine.bias'].clone()
+    other = SegSynthesisBlock(8, 8, w_dim=16, resolution=8, img_channels=6, seg_channels=6, is_last=False)
+    other.load_state_dict(dict(ref))
+    assert torch.equal(other.torgb.weight[:6], w[:6]) and torch.equal(other.torgb.weight[6:], w[6:] * 2)
+    assert torch.equal(other.torgb.bias, torch.cat([b[:6] + 0.5, b[6:] - 0.5]))
+    bad = dict(ref)
+    bad['toseg.affine.bias'] = bad['toseg.affine.bias'] + 1
+    with pytest.raises(RuntimeError, match='toseg'):
+        SegSynthesisBlock(8, 8, w_dim=16, resolution=8, img_channels=6, seg_channels=6, is_last=False).load_state_dict(bad)
