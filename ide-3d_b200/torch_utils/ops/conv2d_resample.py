@@ -18,8 +18,10 @@ def _conv(x, w, stride=1, padding=0, groups=1, transpose=False, flip_weight=True
     return op(x, w, stride=stride, padding=padding, groups=groups)
 
 
-def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, fir_epilogue=None):
-    """fir_epilogue (extension, up > 1 and down == 1 only): keyword arguments of `upfirdn2d.upfirdn2d_epilogue` -- the
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False, fir_epilogue=None, w_transposed=None):
+    """w_transposed (extension, up > 1, groups == 1): `w.transpose(0, 1)` already materialised in the layout cuDNN wants -- the
+    transposed view is not contiguous, so aten copies the whole weight on every call otherwise (9 MB for a 512x512x3x3 layer).
+    fir_epilogue (extension, up > 1 and down == 1 only): keyword arguments of `upfirdn2d.upfirdn2d_epilogue` -- the
     modulated-convolution tail is then applied by the FIR pass that follows the transposed convolution."""
     assert isinstance(x, torch.Tensor) and x.ndim == 4
     assert fir_epilogue is None or (up > 1 and down == 1 and not (int(w.shape[2]) == 1 and int(w.shape[3]) == 1))
@@ -49,7 +51,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
         return _conv(x, w, stride=down, groups=groups, flip_weight=flip_weight)
     if up > 1:                                                          # transposed strided conv, then filter
         if groups == 1:
-            w = w.transpose(0, 1)
+            w = w_transposed if w_transposed is not None else w.transpose(0, 1)
         else:
             w = w.reshape(groups, out_channels // groups, in_per_group, kh, kw).transpose(1, 2)
             w = w.reshape(groups * in_per_group, out_channels // groups, kh, kw)

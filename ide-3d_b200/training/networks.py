@@ -52,7 +52,7 @@ def normalize_2nd_moment(x, dim=1, eps=1e-8):
 
 
 def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, resample_filter=None, demodulate=True,
-                     flip_weight=True, fused_modconv=True, epilogue=None, premodulated=False, dcoefs=None):
+                     flip_weight=True, fused_modconv=True, epilogue=None, premodulated=False, dcoefs=None, w_transposed=None):
     """Style-modulated convolution (inversion/networks.py:55-130).  x [N,I,H,W], weight [O,I,k,k], styles [N,I].
     epilogue (activation-scaled path only): dict(b, act, gain, clamp) -- the bias_act that always follows (:512, :707) is
     then applied here, fused with the demodulation / noise pass (`bias_act.scaled_bias_act`); optional keys next_scale /
@@ -86,7 +86,7 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
             e['act_gain'] = e.pop('gain', None)
             e.update(scale=dcoefs if demodulate else None, noise=noise)
             return conv2d_resample.conv2d_resample(x=x, w=weight.to(x.dtype), f=resample_filter, up=up, down=down,
-                                                   padding=padding, flip_weight=flip_weight, fir_epilogue=e)
+                                                   padding=padding, flip_weight=flip_weight, fir_epilogue=e, w_transposed=w_transposed)
         if (CONV1X1_AS_MATMUL and kh == 1 and kw == 1 and up == 1 and down == 1 and padding == 0 and x.dtype == torch.float32 and x.is_cuda
                 and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous()
                 and not (torch.is_grad_enabled() and (x.requires_grad or weight.requires_grad))):
@@ -227,16 +227,33 @@ class SynthesisLayer(torch.nn.Module):
         noise = None
         if self.use_noise and noise_mode == 'random':
             noise = torch.randn([x.shape[0], 1, self.up * x.shape[2], self.up * x.shape[3]], device=x.device) * self.noise_strength
+        inference = not (torch.is_grad_enabled() and (self.weight.requires_grad or (self.use_noise and self.noise_strength.requires_grad)))
         if self.use_noise and noise_mode == 'const':
-            noise = self.noise_const * self.noise_strength
+            # constants of the weights, cached per parameter version for inference (one multiply / one 9 MB weight copy per layer and step otherwise)
+            noise = self._cached('noise', (self.noise_const, self.noise_strength), lambda: self.noise_const * self.noise_strength) if inference \
+                else self.noise_const * self.noise_strength
         act_gain = self.act_gain * gain
         act_clamp = self.conv_clamp * gain if self.conv_clamp is not None else None
         epilogue = dict(b=self.bias, act=self.activation, gain=act_gain, clamp=act_clamp)
         if next_styles is not None:
             epilogue.update(next_scale=next_styles, only_next=only_next)
+        w_t = None
+        if inference and self.up > 1 and not fused_modconv and x.dtype == self.weight.dtype:
+            fmt = torch.channels_last if CHANNELS_LAST else torch.contiguous_format
+            w_t = self._cached('w_t', (self.weight,), lambda: self.weight.detach().transpose(0, 1).contiguous(memory_format=fmt))
         return modulated_conv2d(x=x, weight=self.weight, styles=styles, noise=noise, up=self.up, padding=self.padding,
                                 resample_filter=self.resample_filter, flip_weight=(self.up == 1), fused_modconv=fused_modconv,
-                                epilogue=epilogue, premodulated=premodulated, dcoefs=None if fused_modconv else dcoefs)
+                                epilogue=epilogue, premodulated=premodulated, dcoefs=None if fused_modconv else dcoefs, w_transposed=w_t)
+
+    def _cached(self, name, tensors, make):
+        """Derived constant of parameters / buffers, recomputed when any of them changes (data pointer, version, device)."""
+        key = tuple((t.data_ptr(), t._version, str(t.device)) for t in tensors)
+        store = self.__dict__.setdefault('_const_cache', {})
+        hit = store.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = store[name] = (key, make())
+        return hit[1]
 
 
 @persistence.persistent_class
