@@ -7,9 +7,10 @@ the published algorithm (Lorensen & Cline 1987), not of PyMCubes' source: cell c
 GENERATED here from first principles (`build_tables`) rather than typed in: per configuration the cut edges are linked into closed loops
 face by face and fan-triangulated; the ambiguous faces (two diagonal inside corners) always separate the inside corners, the same rule
 for both cells that share the face, which makes the surface watertight.  The generated table has the classic shape (820 triangles over
-the 256 configurations, at most 5 per cell).  Conventions follow PyMCubes: volume indexed [x, y, z], vertices in index units, a corner is
-inside where value >= threshold... the orientation / inside test of PyMCubes itself is not recoverable here (parity unpinned; the tests
-pin the geometry instead: watertightness, Euler characteristic, vertices on the iso-level, area / volume of analytic shapes).
+the 256 configurations, at most 5 per cell).  Conventions: volume indexed [x, y, z] and vertices in index units (as PyMCubes documents),
+a corner is inside where value >= threshold, triangle normals point out of the inside region.  PyMCubes' own vertex / triangle order and its
+choices on ambiguous faces are not recoverable here, so parity with it is unpinned; the tests pin the geometry instead (watertightness,
+Euler characteristic, vertices on the iso-level, area / volume of analytic shapes) and the CUDA kernels against the numpy oracle bit for bit.
 
     vertices, triangles = marching_cubes(volume, threshold)      # volume: CUDA tensor [nx, ny, nz] (any float dtype)
 """
