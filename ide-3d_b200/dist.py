@@ -109,6 +109,14 @@ def _pinned_buffer(shape, dtype):
 _shared = {}
 
 
+def _shm_free_bytes():
+    try:
+        st = os.statvfs('/dev/shm')
+        return st.f_bavail * st.f_frsize
+    except OSError:
+        return 0
+
+
 def _shared_frame_buffer(shape, rank, world, tag):
     """One uint8 frame buffer in /dev/shm that EVERY rank of the box maps (torch.from_file, shared) and page-locks
     (cudaHostRegister): each GPU then downloads its own frames straight into rank 0's result over its own PCIe link -- no
@@ -156,6 +164,16 @@ def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, transport='a
     cuda = dev.type == 'cuda'
     if transport == 'auto':
         transport = 'shm' if (cuda and world > 1 and os.path.isdir('/dev/shm')) else 'nccl'
+        if transport == 'shm':
+            # the shared buffer must fit /dev/shm (containers often cap it): rank 0 looks, everybody follows its decision
+            shape_key = (F, G.img_channels, G.img_resolution, G.img_resolution)
+            need = F * G.img_channels * G.img_resolution * G.img_resolution
+            ok = torch.zeros(1, dtype=torch.int32, device=dev)
+            if rank == 0 and ((shape_key, 'frames') in _shared or _shm_free_bytes() > need + (64 << 20)):
+                ok += 1
+            dist.broadcast(ok, src=0)
+            if int(ok.item()) == 0:
+                transport = 'nccl'
     shape = (F, G.img_channels, G.img_resolution, G.img_resolution)
     host = None
     if world > 1 and transport == 'shm':
