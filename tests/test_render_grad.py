@@ -146,3 +146,31 @@ def test_backward_kernel_matches_oracle_autograd(opts, jitter):
     finally:
         render_grad.USE_BACKWARD_KERNEL = True
     assert (t.grad - t2.grad).abs().max() <= tol(gt) and (heads[2][2].grad - heads2[2][2].grad).abs().max() <= tol(w1g)
+
+
+@pytest.mark.gpu
+def test_backward_kernel_planes_only_and_decoder_only():
+    """The two reduced forms of ide3d_raymarch_bwd: gradients for the planes with a frozen decoder (no parameter image in shared memory, the
+    PTI-with-fixed-renderer case) and for the decoder with frozen planes (no scatter); both must equal the corresponding part of the full call."""
+    from ide3d_b200 import render
+    tex, seg, dec, cam = _random_case(2, 16, seed=9)
+    dev = 'cuda'
+    g = torch.Generator().manual_seed(3)
+    gf, gd = torch.randn(2, 30, 51, generator=g).to(dev), torch.randn(2, 30, 1, generator=g).to(dev)
+    base = three_head_from_dense(dec.w1, dec.b1, dec.w2, dec.b2)
+
+    def run(planes_grad, params_grad):
+        t, s = [x.to(dev).requires_grad_(planes_grad) for x in (tex, seg)]
+        heads = [tuple(h[:2]) + tuple(x.to(dev).requires_grad_(params_grad) for x in h[2:]) for h in base]
+        feat, d, _ = render.raymarch(t, s, heads, cam.to(dev), resolution=RES, num_steps=S, jitter_seed=11)
+        (feat * gf).sum().add((d * gd).sum()).backward()
+        return t.grad, s.grad, [x.grad for h in heads for x in h[2:]]
+
+    ft, fs, fp = run(True, True)
+    pt, ps, pp = run(True, False)
+    close = lambda a, b: float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))   # red.add order is not fixed: rounding-level differences
+    assert all(x is None for x in pp) and close(pt, ft) and close(ps, fs)                      # the scatter does not depend on the parameter path
+    dt, ds, dp = run(False, True)
+    assert dt is None and ds is None
+    for a, b in zip(dp, fp):
+        assert (a - b).abs().max() <= 1e-5 * max(1.0, float(b.abs().max()))                        # shared-memory atomics: order-dependent rounding only
