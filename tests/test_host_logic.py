@@ -240,3 +240,25 @@ def test_seg_block_loads_reference_style_torgb_toseg_state_dict():
     bad['toseg.affine.bias'] = bad['toseg.affine.bias'] + 1
     with pytest.raises(RuntimeError, match='toseg'):
         SegSynthesisBlock(8, 8, w_dim=16, resolution=8, img_channels=6, seg_channels=6, is_last=False).load_state_dict(bad)
+
+
+def test_coarse_depths_and_torch_hash_match_the_oracle_on_cpu():
+    """render.coarse_depths (the depths of the first pass of the hierarchical render, computed on the host side of the kernel) equals the
+    oracle's initial_rays + perturb z values, with injected uniforms and with the counter hash (integer-exact twin of the kernel's)."""
+    import numpy as np
+    from ide3d_b200 import render, render_grad
+    from oracle import renderer as orr
+    n, res, S = 2, (5, 4), 11
+    R = res[0] * res[1]
+    seed = 0x0123_4567_89AB_CDEF
+    u_ref = torch.from_numpy(orr.hash_uniform(np.arange(n * R * S, dtype=np.uint64), seed)).reshape(n, R, S)
+    assert torch.equal(render_grad.hash_uniform(n * R * S, seed, 'cpu').reshape(n, R, S), u_ref)
+    pts, zv, d = orr.initial_rays(n, S, 18.0, res, 2.25, 3.3)
+    _, z_ref = orr.perturb(pts, zv, d, u_ref.unsqueeze(-1))
+    z = render.coarse_depths(n, res, S, 2.25, 3.3, jitter_seed=seed, device='cpu')
+    assert z.shape == (n, R, S) and (z - z_ref.reshape(n, R, S)).abs().max() <= 1e-6
+    g = torch.Generator().manual_seed(0)
+    u = torch.rand(n, R, S, generator=g)
+    _, z_ref2 = orr.perturb(pts, zv, d, u.unsqueeze(-1))
+    assert (render.coarse_depths(n, res, S, 2.25, 3.3, jitter_u=u, device='cpu') - z_ref2.reshape(n, R, S)).abs().max() <= 1e-6
+    assert torch.equal(render.coarse_depths(1, res, S, 2.25, 3.3, device='cpu')[0, 0], torch.linspace(2.25, 3.3, S))
