@@ -151,7 +151,8 @@ def stream_frames_sharded(G, ws, c, rank, world, batch=8, out=None, transport='a
     """The frame loop of gen_videos.py:127-139 as a pipeline: frames i = rank, rank+world, ... are rendered in batches and
     copied to page-locked HOST memory on a side stream while the next batch renders.  ws [F, num_ws, w_dim], c [F, 25] on
     the host (pinned for asynchronous uploads).  Returns uint8 [F, 3, H, W] on the host on rank 0, None elsewhere.
-    F must be a multiple of world * batch.
+    F must be a multiple of world * batch.  The returned tensor is a cached buffer (pinned, or the shared one): it is valid until the
+    next call with the same frame count -- consume or copy it before calling again (pass `out=` to get a private copy).
 
     transport (world > 1; how the frames of the other ranks reach rank 0's host memory):
       'shm'   every rank downloads its own frames into ONE shared, page-locked /dev/shm buffer (all ranks on one box): `world`
