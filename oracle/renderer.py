@@ -291,7 +291,8 @@ def render_frames_hierarchical(planes_tex, planes_seg, decoder, cam2world, fov=1
     function but no caller (the generator class is absent), so the COMPOSITION is the one the function's
     docstring prescribes (bins = midpoints of the coarse depths, weights = coarse weights[1:-1]; nerf_pl / pi-GAN order):
     coarse chain -> weights (+1e-5) -> sample_pdf -> fine points = origin + direction * z -> decode -> merge by sorted depth
-    -> composite over all samples.  Parity of the composition is therefore unpinned; every stage in it is a pinned one.
+    -> composite over all samples.  Parity of the ORDER is therefore unpinned; every stage in it is a pinned one, and tests/golden/chain_hier.npz
+    records this order executed with the reference's own stage functions (make_golden.py g_chain_hier).
     importance_u [N*HW, n_importance] injects the uniform draws of sample_pdf (det=True: linspace)."""
     N = planes_tex.shape[0]
     W, H = resolution

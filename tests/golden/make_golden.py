@@ -196,6 +196,49 @@ def g_chain():
     save('voxel', points=pts, out=sv)
 
 
+# ------------------------------------------------------------------ two-pass chain: every stage a reference function
+def g_chain_hier():
+    """The reference tree has sample_pdf (volumetric_rendering.py:224-265) but no caller, so the ORDER below is ours
+    (the one its docstring prescribes); every stage in it -- rays, jitter, world transform, tri-plane gather, compositing,
+    sample_pdf -- is the reference's own function run here."""
+    g = torch.Generator().manual_seed(21)
+    n, S, NI, res = 2, 12, 12, (8, 8)
+    R = res[0] * res[1]
+    tex = torch.randn(n, 96, 16, 16, generator=g)
+    seg = torch.randn(n, 96, 16, 16, generator=g)
+    dec = orr.Decoder.random(hidden=64, seed=8, three_head=True)
+    cam = torch.from_numpy(ocam.look_at_pose(np.array([[1.45], [1.7]], np.float32), np.array([[1.55], [1.6]], np.float32),
+                                             [0, 0, 0.2], radius=2.7, batch_size=2))
+    box_scale = 2.0
+    p, z, d = ref_vr.get_initial_rays_trig(n, S, DEV, 18.0, res, 2.25, 3.3)
+    torch.manual_seed(31)
+    u = torch.rand(z.shape)
+    torch.manual_seed(31)
+    pw, zj, dw, ow, _, _ = ref_vr.transform_sampled_points(p, z, d, DEV, camera=cam)
+    coords = pw.reshape(n, -1, 3) * box_scale
+    raw = dec(ref_triplane(coords, tex), ref_triplane(coords, seg)).reshape(n, R, S, 52)
+    _, _, w = ref_vr.fancy_integration(raw, d, zj, DEV, noise_std=0, clamp_mode='softplus')
+    zf = zj.reshape(n * R, S)
+    mid = 0.5 * (zf[:, :-1] + zf[:, 1:])
+    torch.manual_seed(41)
+    ui = torch.rand(n * R, NI)
+    torch.manual_seed(41)
+    fine = ref_vr.sample_pdf(mid, w.reshape(n * R, S)[:, 1:-1] + 1e-5, NI, det=False).detach().reshape(n, R, NI, 1)
+    fine_pts = ow.unsqueeze(2) + dw.unsqueeze(2) * fine
+    cf = fine_pts.reshape(n, -1, 3) * box_scale
+    raw_f = dec(ref_triplane(cf, tex), ref_triplane(cf, seg)).reshape(n, R, NI, 52)
+    all_z, idx = torch.sort(torch.cat([zj, fine], -2), dim=-2)
+    all_raw = torch.gather(torch.cat([raw, raw_f], -2), -2, idx.expand(-1, -1, -1, 52))
+    rgb, dep, wa = ref_vr.fancy_integration(all_raw, d, all_z, DEV, noise_std=0, clamp_mode='softplus')
+    ro, do_, wo, zo = orr.render_frames_hierarchical(tex, seg, dec, cam, fov=18.0, num_steps=S, n_importance=NI, ray_start=2.25,
+                                                     ray_end=3.3, resolution=res, box_scale=box_scale, jitter_u=u, importance_u=ui)
+    close(all_z, zo, tol=2e-6, what='hier.z'); close(rgb, ro, tol=1e-5, what='hier.rgb')
+    close(dep, do_, tol=1e-5, what='hier.depth'); close(wa, wo, tol=1e-5, what='hier.w')
+    save('chain_hier', planes_tex=tex, planes_seg=seg, w1=dec.w1, b1=dec.b1, w2=dec.w2, b2=dec.b2, camera=cam, u=u, importance_u=ui,
+         box_scale=box_scale, num_steps=S, n_importance=NI, resolution=np.array(res), fine=fine, z_all=all_z, rgb=rgb, depth=dep,
+         weights=wa)
+
+
 # ------------------------------------------------------------------ create_samples quirk
 def g_create_samples():
     src = open(os.path.join(REF, 'extract_shapes.py')).read()
@@ -405,7 +448,7 @@ def g_networks():
 if __name__ == '__main__':
     torch.set_num_threads(4)
     fns = dict(rays=g_rays, transform=g_transform, camera=g_camera, triplane=g_triplane, integration=g_integration, pdf=g_pdf,
-               chain=g_chain, create_samples=g_create_samples, bias_act=g_bias_act, upfirdn2d=g_upfirdn2d,
+               chain=g_chain, chain_hier=g_chain_hier, create_samples=g_create_samples, bias_act=g_bias_act, upfirdn2d=g_upfirdn2d,
                filtered_lrelu=g_filtered_lrelu, conv2d_resample=g_conv2d_resample, networks=g_networks)
     for name in (sys.argv[1:] or list(fns)):              # `make_golden.py networks` regenerates one fixture only
         fns[name]()

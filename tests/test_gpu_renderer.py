@@ -346,6 +346,25 @@ def test_hierarchical_two_pass_matches_oracle_composition(precision):
     assert torch.equal(a[0], b[0]) and a[0].shape == (N, 64, 51)
 
 
+@pytest.mark.parametrize('precision', PRECISIONS)
+def test_hierarchical_matches_recorded_reference_stage_composition(precision):
+    """chain_hier.npz: the two passes composed from the reference's own stage functions (tests/golden/make_golden.py
+    g_chain_hier) vs the fused kernels + ide3d_sample_pdf, same injected uniforms."""
+    from ide3d_b200 import render
+    g = load_golden('chain_hier')
+    res = tuple(int(v) for v in g['resolution'])
+    S, NI = int(g['num_steps']), int(g['n_importance'])
+    heads = three_head_from_dense(g['w1'], g['b1'], g['w2'], g['b2'])
+    feat, depth, w, z = render.raymarch_hierarchical(T(g['planes_tex'], DEV), T(g['planes_seg'], DEV), heads, T(g['camera'], DEV),
+                                                     resolution=res, num_steps=S, n_importance=NI, box_scale=float(g['box_scale']),
+                                                     jitter_u=T(g['u'], DEV), importance_u=T(g['importance_u'], DEV),
+                                                     return_weights=True, return_depths=True, precision=precision)
+    R = res[0] * res[1]
+    assert_close(z, T(g['z_all']).reshape(-1, R, S + NI), 2e-5, what='merged depths')
+    assert_close(feat, g['rgb'], 3 * FEAT_TOL[precision], what='feat'); assert_close(depth, g['depth'], 3 * D_TOL[precision], what='depth')
+    assert_close(w, g['weights'], 3 * W_TOL[precision], what='w')
+
+
 def test_hierarchical_flag_through_the_generator():
     """rendering_kwargs / render_params 'hierarchical' reaches the renderer (forward only)."""
     from ide3d_b200.compat import random_init_generator

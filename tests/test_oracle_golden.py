@@ -212,6 +212,22 @@ def test_networks_restatement_loads_reference_state_dicts_and_reproduces_outputs
                 assert (got - T_(key)).abs().max() < 1e-5, (key, layout)
 
 
+def test_oracle_hierarchical_matches_reference_stage_composition():
+    """chain_hier.npz: two-pass render composed in tests/golden/make_golden.py from the REFERENCE's own stage functions
+    (get_initial_rays_trig, transform_sampled_points, sample_from_triplane, fancy_integration, sample_pdf :224-265)."""
+    from oracle import renderer as orr
+    g = load_golden('chain_hier')
+    dec = orr.Decoder(*[T(g[k]) for k in ('w1', 'b1', 'w2', 'b2')])
+    res = tuple(int(v) for v in g['resolution'])
+    S, NI = int(g['num_steps']), int(g['n_importance'])
+    rgb, depth, w, z = orr.render_frames_hierarchical(T(g['planes_tex']), T(g['planes_seg']), dec, T(g['camera']), num_steps=S,
+                                                      n_importance=NI, resolution=res, box_scale=float(g['box_scale']),
+                                                      jitter_u=T(g['u']), importance_u=T(g['importance_u']))
+    assert (z - T(g['z_all'])).abs().max() < 2e-6
+    assert (rgb - T(g['rgb'])).abs().max() < 1e-5 and (depth - T(g['depth'])).abs().max() < 1e-5
+    assert (w - T(g['weights'])).abs().max() < 1e-5
+
+
 def test_oracle_hierarchical_composition_properties():
     """The two-pass composition around the pinned sample_pdf: merged depths ascending and inside [ray_start - h, ray_end + h],
     S + n_importance samples per ray, weights a sub-probability; importance depths fall where the coarse weights are."""
