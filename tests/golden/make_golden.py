@@ -204,8 +204,11 @@ def g_chain_hier():
     g = torch.Generator().manual_seed(21)
     n, S, NI, res = 2, 12, 12, (8, 8)
     R = res[0] * res[1]
-    tex = torch.randn(n, 96, 16, 16, generator=g)
-    seg = torch.randn(n, 96, 16, 16, generator=g)
+    # band-limited planes (generator planes are smooth): the fine depths are a function of the coarse weights, and white noise would
+    # turn their 1e-6-level differences into feature differences that measure the input's slope, not the implementation
+    smooth = lambda: torch.nn.functional.interpolate(torch.randn(n, 96, 6, 6, generator=g), size=(16, 16), mode='bicubic',
+                                                     align_corners=True).contiguous()
+    tex, seg = smooth(), smooth()
     dec = orr.Decoder.random(hidden=64, seed=8, three_head=True)
     cam = torch.from_numpy(ocam.look_at_pose(np.array([[1.45], [1.7]], np.float32), np.array([[1.55], [1.6]], np.float32),
                                              [0, 0, 0.2], radius=2.7, batch_size=2))
